@@ -1,0 +1,180 @@
+/*
+ * mipgen_b200.h -- C-ABI of the B200-native MIPgen scoring hot path.
+ *
+ * One shared library (libmipgen_b200.so), plain pointers and sizes, no C++ or
+ * torch types.  Every compute entry point runs hand-written sm_100a CUDA
+ * kernels; there is NO CPU fallback -- a missing/failed device is an error
+ * (negative status + mg_last_error()).
+ *
+ * What each entry point replaces in the reference (/root/reference):
+ *
+ *   mg_long_range_content   Featurev5::get_long_range_content      Featurev5.cpp:18-56
+ *   mg_load_svr_model       svm_load_model                         svm.cpp:2759-2973  (mipgen.cpp:409)
+ *   mg_svr_predict          svm_predict / svm_predict_values /     svm.cpp:2580-2593, 2504-2522,
+ *                           Kernel::k_function (RBF)               328-368            (mipgen.cpp:2016)
+ *   mg_score_candidates     SVMipv4::get_score, ::get_parameters   SVMipv4.cpp:114-248, 60-113
+ *                           (+ predict_value)                      mipgen.cpp:1948-2019
+ *   mg_score_regions        the candidate loop nest of             mipgen.cpp:421-501
+ *   mg_panel_*              mipgen::tile_regions + design_mip      mipgen.cpp:599-613
+ *                           (Plus/Minus geometry and setters)      PlusSVMipv4.cpp:7-28, MinusSVMipv4.cpp:6-51
+ *   mg_tile_replay          the score-dependent skips of the loop  mipgen.cpp:426-437, 494-497
+ *
+ * Threading: a context is used by one host thread at a time; calls are
+ * synchronous unless stated.  The library never calls rand()/srand() and never
+ * changes the locale.
+ */
+#ifndef MIPGEN_B200_H
+#define MIPGEN_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MG_NFEAT 192 /* SVMipv4.cpp:13 TOTAL_FEATURES */
+#define MG_NLRC 44   /* Featurev5.h:4 MER_NUM */
+
+/* status codes */
+#define MG_OK 0
+#define MG_ERR_CUDA (-1)    /* CUDA runtime / launch failure, or no usable device */
+#define MG_ERR_INVALID (-2) /* bad argument / inconsistent input */
+#define MG_ERR_MODEL (-3)   /* model file unreadable or not an RBF (epsilon|nu)-SVR */
+#define MG_ERR_NOMODEL (-4) /* SVR requested before a model was loaded */
+#define MG_ERR_NOCONFIG (-5)/* grid call before mg_set_config */
+#define MG_ERR_NOMEM (-6)
+
+/* what to compute (bit mask) */
+#define MG_WANT_LOGISTIC 1 /* SVMipv4::get_score                        */
+#define MG_WANT_SVR 2      /* get_parameters + svm_predict               */
+#define MG_WANT_FEATURES 4 /* the 192 doubles of get_parameters themselves */
+
+typedef struct mg_ctx mg_ctx;
+typedef struct mg_panel mg_panel;
+
+/* The knobs of mipgen.cpp that shape the candidate grid (parse_arg_values, 190-276). */
+typedef struct {
+    int max_capture;       /* -max_capture_size                                   */
+    int min_capture;       /* -min_capture_size                                   */
+    int capture_increment; /* -capture_increment (0 is treated as 1, mipgen.cpp:274) */
+    int max_mip_overlap;   /* -max_mip_overlap, used by the static skip at :429   */
+    int n_pairs;           /* arm pairs in ENUMERATION order: arm sum descending,  */
+    const int *ext_len;    /*   extension length in list order within a sum       */
+    const int *lig_len;    /*   (mipgen.cpp:431, 438; lists built at 222-261)     */
+    int n_oligo_sizes;     /* set<int> oligo_sizes (mipgen.cpp:77); may be 0      */
+    const int *oligo_sizes;
+} mg_config;
+
+/* One Featurev5 (Featurev5.h:10-23).  Coordinates are 1-based inclusive. */
+typedef struct {
+    const char *seq;   /* chromosomal_sequence (upper-cased by the caller, may hold N/IUPAC/-) */
+    int seq_len;       /* must equal seq_stop - seq_start + 1                                 */
+    int seq_start;     /* chromosomal_sequence_start_position                                 */
+    int seq_stop;      /* chromosomal_sequence_stop_position                                  */
+    int start_flanked; /* start_position_flanked                                              */
+    int stop_flanked;  /* stop_position_flanked                                               */
+    const double *lrc; /* long_range_content[44], or NULL (logistic only / zeros)            */
+    const int *copies; /* [n_oligo_sizes][seq_len]: copy number of the oligo of size
+                          oligo_sizes[k] starting at seq index i (copy_chr_start_stop,
+                          mipgen.cpp:83, 612-613; 0 = absent key); NULL => every copy is 1   */
+} mg_region;
+
+/* One SVMipv4 object as mipgen.cpp leaves it after design_mip: strand-oriented strings
+ * (already reverse-complemented on '-'), constructor lengths and copy numbers. */
+typedef struct {
+    const char *ext; int ext_n; /* ext_probe_sequence   */
+    const char *lig; int lig_n; /* lig_probe_sequence   */
+    const char *tgt; int tgt_n; /* scan_target_sequence */
+    int ext_len, lig_len, scan_size;
+    int ext_copy, lig_copy;
+} mg_candidate;
+
+/* Per-kernel device timings (CUDA events on the launching stream) accumulated since
+ * the last mg_reset_timings().  ms_* are sums over launches. */
+typedef struct {
+    double ms_feat;  long launches_feat;   /* K-feat (+ fused logistic epilogue)      */
+    double ms_svr;   long launches_svr;    /* K-svr  (FP64 DMMA contraction + exp)     */
+    double ms_other; long launches_other;  /* encode / lrc / misc                      */
+    long candidates_feat, candidates_svr;  /* units the timed launches processed       */
+} mg_timings;
+
+/* ---- context ---------------------------------------------------------------- */
+const char *mg_version(void);
+/* Create a context on CUDA device `device`.  Fails (MG_ERR_CUDA) without a GPU. */
+int mg_create(int device, mg_ctx **out);
+void mg_destroy(mg_ctx *ctx);
+const char *mg_last_error(const mg_ctx *ctx); /* ctx may be NULL: last create error */
+int mg_set_config(mg_ctx *ctx, const mg_config *cfg);
+int mg_sync(mg_ctx *ctx);
+/* Device stopwatch on the context's stream: start records a CUDA event, stop records a
+ * second one, waits for it and returns the elapsed device time in milliseconds. */
+int mg_timer_start(mg_ctx *ctx);
+int mg_timer_stop(mg_ctx *ctx, double *ms);
+int mg_reset_timings(mg_ctx *ctx);
+int mg_get_timings(mg_ctx *ctx, mg_timings *out); /* synchronises the stream */
+
+/* ---- SVR model ---------------------------------------------------------------- */
+/* Parse a libsvm text model (svm.cpp:2759-2973) and upload it as a dense SV matrix. */
+int mg_load_svr_model(mg_ctx *ctx, const char *path);
+/* Same, from memory: sv is [n_sv][n_feat] row-major (n_feat <= 192). */
+int mg_set_svr_model(mg_ctx *ctx, const double *sv, const double *alpha, int n_sv, int n_feat,
+                     double gamma, double rho);
+int mg_model_info(const mg_ctx *ctx, int *n_sv, double *gamma, double *rho);
+/* svm_predict for n dense rows x[i*ld .. i*ld+191] (features 1..192). out[n]. */
+int mg_svr_predict(mg_ctx *ctx, const double *x, long n, long ld, double *out);
+/* Same arithmetic order as libsvm (direct (x-s)^2 form, sequential sums), one thread
+ * per row: the slow on-device cross-check of the contraction kernel. */
+int mg_svr_predict_direct(mg_ctx *ctx, const double *x, long n, long ld, double *out);
+
+/* ---- per-region constants -------------------------------------------------------- */
+/* long_range_content of one region: ext_seq is the region +- (max_capture+1000) window,
+ * denom = seq_stop - seq_start + 2001 (Featurev5.cpp:49,53). */
+int mg_long_range_content(mg_ctx *ctx, const char *ext_seq, int n, int denom, double out[MG_NLRC]);
+
+/* ---- explicit candidates (the SVMipv4 interface) --------------------------------- */
+/* lrc: [n][44] (one row per candidate) or NULL.  Any output may be NULL when not wanted.
+ * logistic[n], svr[n], features[n][192]. */
+int mg_score_candidates(mg_ctx *ctx, const mg_candidate *cands, long n, const double *lrc, int want,
+                        double *logistic, double *svr, double *features);
+
+/* ---- region grids (the tile_regions loop nest) ------------------------------------- */
+/* Grid of one region, canonical (= reference enumeration) order:
+ *   index = (((scan_idx*n_cap + cap_idx)*n_pairs + pair_idx)*2 + strand)      strand 0 '+', 1 '-'
+ *   scan_start = first_scan_start + scan_idx, capture = max_capture - cap_idx*increment  */
+int64_t mg_grid_size(const mg_ctx *ctx, const mg_region *r);
+int mg_first_scan_start(const mg_ctx *ctx, const mg_region *r);
+/* the same two, from a bare config (pure host arithmetic, no device needed) */
+int64_t mg_config_grid_size(const mg_config *cfg, const mg_region *r);
+int mg_config_first_scan_start(const mg_config *cfg, const mg_region *r);
+
+/* Host-buffer call: upload regions, score every grid point on the device, copy back.
+ * Region i's grid starts at offsets[i] (offsets may be NULL; out_offsets, if given,
+ * receives n+1 prefix sums).  valid[i]=0 marks points removed by the static skips
+ * (mipgen.cpp:429, 443-444); their scores are NaN. */
+int mg_score_regions(mg_ctx *ctx, const mg_region *regions, int n, int want, int64_t *out_offsets,
+                     uint8_t *valid, double *logistic, double *svr, double *features);
+
+/* Device-resident variant: inputs are uploaded once, results stay in HBM. */
+int mg_panel_create(mg_ctx *ctx, const mg_region *regions, int n, mg_panel **out);
+void mg_panel_destroy(mg_panel *p);
+int64_t mg_panel_candidates(const mg_panel *p);
+int64_t mg_panel_valid_candidates(const mg_panel *p); /* statically valid grid points */
+/* Launch the kernels for the whole panel on the context's stream (asynchronous). */
+int mg_panel_score(mg_ctx *ctx, mg_panel *p, int want);
+/* Copy results back (synchronous).  features may be NULL. */
+int mg_panel_fetch(mg_ctx *ctx, mg_panel *p, uint8_t *valid, double *logistic, double *svr, double *features);
+/* Raw device pointers of the result arrays (NULL if never computed). */
+int mg_panel_device_ptrs(const mg_panel *p, const uint8_t **valid, const double **logistic, const double **svr);
+
+/* ---- host helper: replay of the score-dependent control flow ---------------------- */
+/* Walks one scored region grid exactly like the tile loop (mipgen.cpp:426-497) and
+ * writes the grid indices the reference would have enumerated.  method: 0 logistic,
+ * 1 svr, 2 mixed; heuristic: -logistic_heuristic != "off".  Returns the count, or -1 on
+ * a bad config.  Pure host logic: needs no context and no device. */
+int64_t mg_tile_replay(const mg_config *cfg, const mg_region *r, const uint8_t *valid, const double *score,
+                       int method, int heuristic, double upper_score_limit, int64_t *out_idx, int64_t cap);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MIPGEN_B200_H */

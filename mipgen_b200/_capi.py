@@ -1,0 +1,335 @@
+"""ctypes binding of include/mipgen_b200.h -- the same C-ABI a cgo/JNI/C++ caller binds.
+
+Loading fails loudly when libmipgen_b200.so is missing; creating a Context fails
+loudly when there is no CUDA device.  There is no CPU fallback anywhere.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import List, Optional, Sequence
+
+import numpy as np
+
+from .panel import Config, Region
+
+LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "libmipgen_b200.so")
+
+MG_WANT_LOGISTIC, MG_WANT_SVR, MG_WANT_FEATURES = 1, 2, 4
+MG_NFEAT, MG_NLRC = 192, 44
+
+c_double_p = C.POINTER(C.c_double)
+c_int_p = C.POINTER(C.c_int)
+c_ubyte_p = C.POINTER(C.c_ubyte)
+c_int64_p = C.POINTER(C.c_int64)
+
+
+class MgConfig(C.Structure):
+    _fields_ = [("max_capture", C.c_int), ("min_capture", C.c_int), ("capture_increment", C.c_int),
+                ("max_mip_overlap", C.c_int), ("n_pairs", C.c_int), ("ext_len", c_int_p),
+                ("lig_len", c_int_p), ("n_oligo_sizes", C.c_int), ("oligo_sizes", c_int_p)]
+
+
+class MgRegion(C.Structure):
+    _fields_ = [("seq", C.c_char_p), ("seq_len", C.c_int), ("seq_start", C.c_int), ("seq_stop", C.c_int),
+                ("start_flanked", C.c_int), ("stop_flanked", C.c_int), ("lrc", c_double_p),
+                ("copies", c_int_p)]
+
+
+class MgCandidate(C.Structure):
+    _fields_ = [("ext", C.c_char_p), ("ext_n", C.c_int), ("lig", C.c_char_p), ("lig_n", C.c_int),
+                ("tgt", C.c_char_p), ("tgt_n", C.c_int), ("ext_len", C.c_int), ("lig_len", C.c_int),
+                ("scan_size", C.c_int), ("ext_copy", C.c_int), ("lig_copy", C.c_int)]
+
+
+class MgTimings(C.Structure):
+    _fields_ = [("ms_feat", C.c_double), ("launches_feat", C.c_long), ("ms_svr", C.c_double),
+                ("launches_svr", C.c_long), ("ms_other", C.c_double), ("launches_other", C.c_long),
+                ("candidates_feat", C.c_long), ("candidates_svr", C.c_long)]
+
+
+# every symbol include/mipgen_b200.h declares: (name, restype, argtypes)
+SYMBOLS = [
+    ("mg_version", C.c_char_p, []),
+    ("mg_create", C.c_int, [C.c_int, C.POINTER(C.c_void_p)]),
+    ("mg_destroy", None, [C.c_void_p]),
+    ("mg_last_error", C.c_char_p, [C.c_void_p]),
+    ("mg_set_config", C.c_int, [C.c_void_p, C.POINTER(MgConfig)]),
+    ("mg_sync", C.c_int, [C.c_void_p]),
+    ("mg_timer_start", C.c_int, [C.c_void_p]),
+    ("mg_timer_stop", C.c_int, [C.c_void_p, c_double_p]),
+    ("mg_reset_timings", C.c_int, [C.c_void_p]),
+    ("mg_get_timings", C.c_int, [C.c_void_p, C.POINTER(MgTimings)]),
+    ("mg_load_svr_model", C.c_int, [C.c_void_p, C.c_char_p]),
+    ("mg_set_svr_model", C.c_int, [C.c_void_p, c_double_p, c_double_p, C.c_int, C.c_int, C.c_double, C.c_double]),
+    ("mg_model_info", C.c_int, [C.c_void_p, c_int_p, c_double_p, c_double_p]),
+    ("mg_svr_predict", C.c_int, [C.c_void_p, c_double_p, C.c_long, C.c_long, c_double_p]),
+    ("mg_svr_predict_direct", C.c_int, [C.c_void_p, c_double_p, C.c_long, C.c_long, c_double_p]),
+    ("mg_long_range_content", C.c_int, [C.c_void_p, C.c_char_p, C.c_int, C.c_int, c_double_p]),
+    ("mg_score_candidates", C.c_int, [C.c_void_p, C.POINTER(MgCandidate), C.c_long, c_double_p, C.c_int,
+                                      c_double_p, c_double_p, c_double_p]),
+    ("mg_grid_size", C.c_int64, [C.c_void_p, C.POINTER(MgRegion)]),
+    ("mg_first_scan_start", C.c_int, [C.c_void_p, C.POINTER(MgRegion)]),
+    ("mg_config_grid_size", C.c_int64, [C.POINTER(MgConfig), C.POINTER(MgRegion)]),
+    ("mg_config_first_scan_start", C.c_int, [C.POINTER(MgConfig), C.POINTER(MgRegion)]),
+    ("mg_score_regions", C.c_int, [C.c_void_p, C.POINTER(MgRegion), C.c_int, C.c_int, c_int64_p, c_ubyte_p,
+                                   c_double_p, c_double_p, c_double_p]),
+    ("mg_panel_create", C.c_int, [C.c_void_p, C.POINTER(MgRegion), C.c_int, C.POINTER(C.c_void_p)]),
+    ("mg_panel_destroy", None, [C.c_void_p]),
+    ("mg_panel_candidates", C.c_int64, [C.c_void_p]),
+    ("mg_panel_valid_candidates", C.c_int64, [C.c_void_p]),
+    ("mg_panel_score", C.c_int, [C.c_void_p, C.c_void_p, C.c_int]),
+    ("mg_panel_fetch", C.c_int, [C.c_void_p, C.c_void_p, c_ubyte_p, c_double_p, c_double_p, c_double_p]),
+    ("mg_panel_device_ptrs", C.c_int, [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(C.c_void_p)]),
+    ("mg_tile_replay", C.c_int64, [C.POINTER(MgConfig), C.POINTER(MgRegion), c_ubyte_p, c_double_p, C.c_int, C.c_int,
+                                   C.c_double, c_int64_p, C.c_int64]),
+]
+
+_lib = None
+
+
+def load_library() -> C.CDLL:
+    """dlopen the in-tree library and bind every declared symbol (raises if any is missing)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(
+                "%s is missing: run `python -c 'import __graft_entry__ as g; g.build()'` (needs nvcc). "
+                "mipgen_b200 has no CPU fallback." % LIB_PATH)
+        lib = C.CDLL(LIB_PATH)
+        for name, res, args in SYMBOLS:
+            fn = getattr(lib, name)  # AttributeError if the symbol is not exported
+            fn.restype = res
+            fn.argtypes = args
+        _lib = lib
+    return _lib
+
+
+class MgError(RuntimeError):
+    pass
+
+
+def _ptr(a: Optional[np.ndarray], t):
+    return a.ctypes.data_as(t) if a is not None else t()
+
+
+def _c_config(cfg: Config):
+    e = np.asarray(cfg.ext_len, np.int32)
+    l = np.asarray(cfg.lig_len, np.int32)
+    o = np.asarray(cfg.oligo_sizes, np.int32)
+    c = MgConfig(cfg.max_capture, cfg.min_capture, cfg.capture_increment, cfg.max_mip_overlap, len(e),
+                 _ptr(e, c_int_p), _ptr(l, c_int_p), len(o), _ptr(o, c_int_p))
+    return c, (e, l, o)
+
+
+def _c_regions(regions: Sequence[Region]):
+    keep = []
+    arr = (MgRegion * max(len(regions), 1))()
+    for i, r in enumerate(regions):
+        lrc = np.ascontiguousarray(r.lrc, np.float64) if r.lrc is not None else None
+        cop = np.ascontiguousarray(r.copies, np.int32) if r.copies is not None else None
+        keep += [lrc, cop, r.seq]
+        arr[i] = MgRegion(r.seq, len(r.seq), r.seq_start, r.seq_stop, r.start_flanked, r.stop_flanked,
+                          _ptr(lrc, c_double_p), _ptr(cop, c_int_p))
+    return arr, keep
+
+
+def config_grid_size(cfg: Config, r: Region) -> int:
+    """Host arithmetic only (no device): size of a region's candidate grid."""
+    c, _k = _c_config(cfg)
+    arr, _k2 = _c_regions([r])
+    return int(load_library().mg_config_grid_size(C.byref(c), arr))
+
+
+def tile_replay(cfg: Config, r: Region, valid: np.ndarray, score: np.ndarray, method: int, heuristic: bool,
+                upper: float) -> np.ndarray:
+    """Host replay of the tile loop's score-dependent skips (mg_tile_replay; no device needed)."""
+    c, _k = _c_config(cfg)
+    arr, _k2 = _c_regions([r])
+    out = np.empty(valid.size, np.int64)
+    valid = np.ascontiguousarray(valid, np.uint8)
+    score = np.ascontiguousarray(score, np.float64)
+    n = load_library().mg_tile_replay(C.byref(c), arr, _ptr(valid, c_ubyte_p), _ptr(score, c_double_p), method,
+                                      int(heuristic), upper, _ptr(out, c_int64_p), out.size)
+    if n < 0:
+        raise MgError("mg_tile_replay: bad config")
+    return out[:n]
+
+
+class Panel:
+    """Regions resident in HBM (mg_panel)."""
+
+    def __init__(self, ctx: "Context", handle, offsets: np.ndarray, keep):
+        self.ctx, self.h, self.offsets, self._keep = ctx, handle, offsets, keep
+
+    @property
+    def n_candidates(self) -> int:
+        return int(self.ctx.lib.mg_panel_candidates(self.h))
+
+    def valid_candidates(self) -> int:
+        return int(self.ctx.lib.mg_panel_valid_candidates(self.h))
+
+    def score(self, want: int) -> None:
+        """Launch the kernels for the whole panel (asynchronous on the context's stream)."""
+        self.ctx._check(self.ctx.lib.mg_panel_score(self.ctx.h, self.h, want))
+
+    def fetch(self, valid=True, logistic=False, svr=False, features=False):
+        n = self.n_candidates
+        v = np.empty(n, np.uint8) if valid else None
+        lo = np.empty(n, np.float64) if logistic else None
+        sv = np.empty(n, np.float64) if svr else None
+        ft = np.empty((n, MG_NFEAT), np.float64) if features else None
+        self.ctx._check(self.ctx.lib.mg_panel_fetch(self.ctx.h, self.h, _ptr(v, c_ubyte_p), _ptr(lo, c_double_p),
+                                                    _ptr(sv, c_double_p), _ptr(ft, c_double_p)))
+        return v, lo, sv, ft
+
+    def fetch_into(self, valid: Optional[np.ndarray], logistic: Optional[np.ndarray], svr: Optional[np.ndarray]) -> None:
+        self.ctx._check(self.ctx.lib.mg_panel_fetch(self.ctx.h, self.h, _ptr(valid, c_ubyte_p), _ptr(logistic, c_double_p),
+                                                    _ptr(svr, c_double_p), c_double_p()))
+
+    def close(self) -> None:
+        if self.h:
+            self.ctx.lib.mg_panel_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class Context:
+    """One mg_ctx on one CUDA device."""
+
+    def __init__(self, device: int = 0):
+        self.lib = load_library()
+        h = C.c_void_p()
+        rc = self.lib.mg_create(device, C.byref(h))
+        if rc != 0:
+            raise MgError("mg_create(%d) failed (%d): %s" % (device, rc, self.lib.mg_last_error(None).decode()))
+        self.h = h
+        self.cfg: Optional[Config] = None
+        self._cfg_keep = None
+
+    def close(self) -> None:
+        if getattr(self, "h", None):
+            self.lib.mg_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc: int) -> None:
+        if rc != 0:
+            raise MgError("mipgen_b200 error %d: %s" % (rc, self.lib.mg_last_error(self.h).decode()))
+
+    # -- configuration / model ----------------------------------------------
+    def set_config(self, cfg: Config) -> None:
+        c, _keep = _c_config(cfg)
+        self._check(self.lib.mg_set_config(self.h, C.byref(c)))
+        self.cfg = cfg
+
+    def load_svr_model(self, path: str) -> None:
+        self._check(self.lib.mg_load_svr_model(self.h, path.encode()))
+
+    def set_svr_model(self, sv: np.ndarray, alpha: np.ndarray, gamma: float, rho: float) -> None:
+        sv = np.ascontiguousarray(sv, np.float64)
+        alpha = np.ascontiguousarray(alpha, np.float64)
+        self._check(self.lib.mg_set_svr_model(self.h, _ptr(sv, c_double_p), _ptr(alpha, c_double_p), sv.shape[0],
+                                              sv.shape[1], gamma, rho))
+
+    def model_info(self):
+        n, g, r = C.c_int(), C.c_double(), C.c_double()
+        self._check(self.lib.mg_model_info(self.h, C.byref(n), C.byref(g), C.byref(r)))
+        return n.value, g.value, r.value
+
+    # -- timings ---------------------------------------------------------------
+    def sync(self) -> None:
+        self._check(self.lib.mg_sync(self.h))
+
+    def timer_start(self) -> None:
+        self._check(self.lib.mg_timer_start(self.h))
+
+    def timer_stop(self) -> float:
+        ms = C.c_double()
+        self._check(self.lib.mg_timer_stop(self.h, C.byref(ms)))
+        return ms.value
+
+    def reset_timings(self) -> None:
+        self._check(self.lib.mg_reset_timings(self.h))
+
+    def timings(self) -> MgTimings:
+        t = MgTimings()
+        self._check(self.lib.mg_get_timings(self.h, C.byref(t)))
+        return t
+
+    # -- scoring ---------------------------------------------------------------
+    def svr_predict(self, X: np.ndarray, direct: bool = False) -> np.ndarray:
+        X = np.ascontiguousarray(X, np.float64)
+        out = np.empty(X.shape[0], np.float64)
+        f = self.lib.mg_svr_predict_direct if direct else self.lib.mg_svr_predict
+        self._check(f(self.h, _ptr(X, c_double_p), X.shape[0], X.shape[1], _ptr(out, c_double_p)))
+        return out
+
+    def long_range_content(self, flank_seq: bytes, seq_start: int, seq_stop: int) -> np.ndarray:
+        out = np.empty(MG_NLRC, np.float64)
+        self._check(self.lib.mg_long_range_content(self.h, flank_seq, len(flank_seq), seq_stop - seq_start + 2001,
+                                                   _ptr(out, c_double_p)))
+        return out
+
+    def score_candidates(self, cands: Sequence[dict], lrc: Optional[np.ndarray] = None, want: int = MG_WANT_LOGISTIC):
+        """cands: dicts with ext/lig/tgt bytes (strand-oriented) and optional ext_len, lig_len,
+        scan_size, ext_copy, lig_copy -- the fields of an SVMipv4 object."""
+        n = len(cands)
+        arr = (MgCandidate * max(n, 1))()
+        for i, c in enumerate(cands):
+            arr[i] = MgCandidate(c["ext"], len(c["ext"]), c["lig"], len(c["lig"]), c["tgt"], len(c["tgt"]),
+                                 c.get("ext_len", len(c["ext"])), c.get("lig_len", len(c["lig"])),
+                                 c.get("scan_size", len(c["tgt"])), c.get("ext_copy", 1), c.get("lig_copy", 1))
+        lrc_a = np.ascontiguousarray(lrc, np.float64) if lrc is not None else None
+        lo = np.empty(n, np.float64) if want & MG_WANT_LOGISTIC else None
+        sv = np.empty(n, np.float64) if want & MG_WANT_SVR else None
+        ft = np.empty((n, MG_NFEAT), np.float64) if want & MG_WANT_FEATURES else None
+        self._check(self.lib.mg_score_candidates(self.h, arr, n, _ptr(lrc_a, c_double_p), want, _ptr(lo, c_double_p),
+                                                 _ptr(sv, c_double_p), _ptr(ft, c_double_p)))
+        return lo, sv, ft
+
+    def _regions(self, regions: Sequence[Region]):
+        return _c_regions(regions)
+
+    def grid_size(self, r: Region) -> int:
+        arr, _keep = self._regions([r])
+        return int(self.lib.mg_grid_size(self.h, arr))
+
+    def score_regions(self, regions: Sequence[Region], want: int = MG_WANT_LOGISTIC, out=None):
+        """Host-buffer call (H2D + kernels + D2H inside).  Returns offsets, valid, logistic, svr, features."""
+        arr, _keep = self._regions(regions)
+        n = len(regions)
+        offsets = np.zeros(n + 1, np.int64)
+        for i in range(n):
+            offsets[i + 1] = offsets[i] + self.lib.mg_grid_size(self.h, C.byref(arr[i]))
+        total = int(offsets[-1])
+        if out is not None:
+            valid, lo, sv, ft = out
+        else:
+            valid = np.empty(total, np.uint8)
+            lo = np.empty(total, np.float64) if want & MG_WANT_LOGISTIC else None
+            sv = np.empty(total, np.float64) if want & MG_WANT_SVR else None
+            ft = np.empty((total, MG_NFEAT), np.float64) if want & MG_WANT_FEATURES else None
+        self._check(self.lib.mg_score_regions(self.h, arr, n, want, _ptr(offsets, c_int64_p), _ptr(valid, c_ubyte_p),
+                                              _ptr(lo, c_double_p), _ptr(sv, c_double_p), _ptr(ft, c_double_p)))
+        return offsets, valid, lo, sv, ft
+
+    def panel(self, regions: Sequence[Region]) -> Panel:
+        arr, keep = self._regions(regions)
+        n = len(regions)
+        offsets = np.zeros(n + 1, np.int64)
+        for i in range(n):
+            offsets[i + 1] = offsets[i] + self.lib.mg_grid_size(self.h, C.byref(arr[i]))
+        h = C.c_void_p()
+        self._check(self.lib.mg_panel_create(self.h, arr, n, C.byref(h)))
+        return Panel(self, h, offsets, keep)

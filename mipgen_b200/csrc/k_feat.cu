@@ -1,0 +1,494 @@
+// k_feat.cu -- K-feat (+ fused logistic epilogue), K-encode, K-lrc.
+//
+// K-feat restates, for the GPU, what the reference does per candidate in
+//   tile_regions / design_mip          mipgen.cpp:446-462, 602-613
+//   Plus/MinusSVMipv4 geometry         PlusSVMipv4.cpp:7-28, MinusSVMipv4.cpp:6-51
+//   SVMipv4::get_parameters            SVMipv4.cpp:60-113   (192 FP64 features)
+//   SVMipv4::get_score                 SVMipv4.cpp:114-248  (logistic score)
+//
+// Mapping: one warp owns 32 consecutive candidates.  For each of them the 32 lanes
+// count k-mers cooperatively (one shared-memory atomic per base: every base votes for
+// its "extended trimer" (X, Y|none, Z|none); di- and mono-nucleotide counts are sums of
+// those bins), derive the count slots, and write the candidate's 192-double feature row
+// with six coalesced 256-byte stores.  The minus strand is never materialised: counts
+// are taken on the genomic window and looked up through the reverse-complement k-mer
+// slot.  Lane c keeps the handful of integers the logistic model needs for candidate c;
+// after 32 candidates every lane evaluates one 70-term polynomial, so the epilogue runs
+// at full lane occupancy and the scores leave as one coalesced 256-byte store.
+//
+// All feature values are a single IEEE division of two small integers, and the logistic
+// exponent is summed in the reference's order with explicit round-to-nearest mul/add
+// (no FMA contraction), so both are bit-identical to the CPU code; only pow() differs
+// (CUDA vs glibc, <= 2 ulp).
+#include "mg_common.cuh"
+#include "logistic_terms.inc"
+
+namespace {
+
+constexpr int kWarpsPerBlock = 8;
+constexpr int kHistInts = 128;  // 84 insert bins + 20 ext + 20 lig (+4 pad)
+constexpr int kWarpSmemInts = kHistInts + SLOT_COUNT;
+
+struct View {
+    const uint8_t *ext, *lig, *tgt;  // windows in genomic orientation
+    int ext_n, lig_n, tgt_n;         // characters actually present (substr clamps)
+    int ext_len, lig_len, scan_size; // constructor values: the divisors
+    int rc;                          // 1: the stored strings are reverse complements of the windows
+    int ext_copy, lig_copy;
+    const double *lrc;               // [44] or null
+    int ok;                          // 0: statically skipped grid point
+};
+
+struct Stash {  // what the logistic model needs, kept by lane c for candidate c
+    int eg, ec, ea, lg, lc, la, tg, tc, ta;
+    int runs, ext_len, lig_len, scan_size, jcode, ext_copy, lig_copy, state;  // state: 0 skipped, 1 invalid, 2 ok
+};
+
+__device__ __forceinline__ int base_class(uint32_t c)
+{
+    // G/C -> 0, A/T -> 1, anything else -> 2   (SVMipv4.cpp:123-139)
+    return (c == B_C || c == B_G) ? 0 : ((c == B_A || c == B_T) ? 1 : 2);
+}
+
+__device__ __forceinline__ double log_copy(int copy, const double *__restrict__ tab)
+{
+    // SVMipv4.cpp:109-110 / 173-174.  tab = glibc log10 of 0..100 computed on the host.
+    if (copy > 100) return 2.0;
+    if (copy < 0) return __longlong_as_double(0xfff8000000000000LL);
+    return tab[copy];
+}
+
+// Count one arm window into hist[20] (bin = X*5 + (Y|none)).  Returns flag bits: 1 = has 'N', 2 = has '-'.
+__device__ __forceinline__ uint32_t count_arm(const uint8_t *__restrict__ w, int n, int *hist, int lane)
+{
+    uint32_t flags = 0;
+    for (int p0 = 0; p0 < n; p0 += 32) {
+        int p = p0 + lane;
+        uint32_t c0 = B_NONE, c1 = B_NONE;
+        if (p < n) {
+            c0 = w[p];
+            if (p + 1 < n) c1 = w[p + 1];
+        }
+        if (c0 < 4) atomicAdd(&hist[c0 * 5 + (c1 < 4 ? c1 : 4)], 1);
+        if (__any_sync(0xffffffffu, c0 == B_N)) flags |= 1;
+        if (__any_sync(0xffffffffu, c0 == B_DASH)) flags |= 2;
+    }
+    return flags;
+}
+
+// Process one candidate with the whole warp.  sm: this warp's kWarpSmemInts ints.
+__device__ __forceinline__ void warp_candidate(const View &v, int *sm, int lane, const uint32_t (&fd)[6],
+                                               const double *__restrict__ logtab, double *__restrict__ xrow,
+                                               Stash &st, bool mine)
+{
+    int *hist_ins = sm, *hist_ext = sm + 84, *hist_lig = sm + 104, *slot = sm + kHistInts;
+
+    if (!v.ok) {
+        if (mine) st.state = 0;
+        if (xrow) {
+#pragma unroll
+            for (int m = 0; m < 6; m++) xrow[lane + 32 * m] = 0.0;
+        }
+        return;
+    }
+
+#pragma unroll
+    for (int i = 0; i < kHistInts / 32; i++) sm[lane + 32 * i] = 0;
+    __syncwarp();
+
+    // ---- insert: extended-trimer histogram, class transitions, "other" detection ----
+    int trans = 0;
+    bool any_other = false;
+    for (int p0 = 0; p0 < v.tgt_n; p0 += 32) {
+        int p = p0 + lane;
+        uint32_t c0 = B_NONE, c1 = B_NONE, c2 = B_NONE, cm = B_NONE;
+        if (p < v.tgt_n) {
+            c0 = v.tgt[p];
+            if (p + 1 < v.tgt_n) c1 = v.tgt[p + 1];
+            if (p + 2 < v.tgt_n) c2 = v.tgt[p + 2];
+            if (p > 0) cm = v.tgt[p - 1];
+        }
+        if (c0 < 4) {
+            int bin = (c1 < 4) ? (int)(c0 * 21 + c1 * 5 + (c2 < 4 ? c2 : 4)) : (int)(c0 * 21 + 20);
+            atomicAdd(&hist_ins[bin], 1);
+        }
+        bool in = p < v.tgt_n;
+        trans += __popc(__ballot_sync(0xffffffffu, in && p > 0 && base_class(c0) != base_class(cm)));
+        any_other |= __any_sync(0xffffffffu, in && c0 >= 4) != 0;
+    }
+    uint32_t fe = count_arm(v.ext, v.ext_n, hist_ext, lane);
+    uint32_t fl = count_arm(v.lig, v.lig_n, hist_lig, lane);
+    __syncwarp();
+
+    // ---- derive count slots (genomic orientation) ----
+#pragma unroll
+    for (int t = lane; t < 64; t += 32) slot[SLOT_INS_TRI + t] = hist_ins[(t >> 4) * 21 + ((t >> 2) & 3) * 5 + (t & 3)];
+    if (lane < 16) {
+        int X = lane >> 2, Y = lane & 3, s = 0;
+#pragma unroll
+        for (int z = 0; z < 5; z++) s += hist_ins[X * 21 + Y * 5 + z];
+        slot[SLOT_INS_DI + lane] = s;
+        slot[SLOT_EXT_DI + lane] = hist_ext[X * 5 + Y];
+        slot[SLOT_LIG_DI + lane] = hist_lig[X * 5 + Y];
+    } else if (lane < 20) {
+        int X = lane - 16, s = hist_ins[X * 21 + 20], se = 0, sl = 0;
+#pragma unroll
+        for (int y = 0; y < 20; y++) s += hist_ins[X * 21 + y];
+#pragma unroll
+        for (int y = 0; y < 5; y++) { se += hist_ext[X * 5 + y]; sl += hist_lig[X * 5 + y]; }
+        slot[SLOT_INS_MONO + X] = s;
+        slot[SLOT_EXT_MONO + X] = se;
+        slot[SLOT_LIG_MONO + X] = sl;
+    }
+    __syncwarp();
+    if (lane == 0) {
+        slot[SLOT_INS_GC] = slot[SLOT_INS_MONO + B_C] + slot[SLOT_INS_MONO + B_G];
+        slot[SLOT_EXT_GC] = slot[SLOT_EXT_MONO + B_C] + slot[SLOT_EXT_MONO + B_G];
+        slot[SLOT_LIG_GC] = slot[SLOT_LIG_MONO + B_C] + slot[SLOT_LIG_MONO + B_G];
+    }
+    __syncwarp();
+
+    // ---- ligation junction: first two characters of the (oriented) ligation arm ----
+    int jcode = -1;
+    if (v.lig_n >= 2) {
+        uint32_t j0 = v.rc ? v.lig[v.lig_n - 1] : v.lig[0];
+        uint32_t j1 = v.rc ? v.lig[v.lig_n - 2] : v.lig[1];
+        if (j0 < 4 && j1 < 4) jcode = v.rc ? (int)((3 - j0) * 4 + (3 - j1)) : (int)(j0 * 4 + j1);
+    }
+    // 'N' in an arm, or '-' in mip_seq (== '-' in an arm)   SVMipv4.cpp:63, 116
+    bool invalid = ((fe | fl) & 3) != 0;
+
+    // ---- run count (SVMipv4.cpp:118-141) ----
+    int runs = trans + 1;
+    if (any_other && !invalid) {
+        // characters outside ACGT make the reference's state machine order dependent:
+        // replay it literally, in stored-string order (lane 0; rare path)
+        int r = 0;
+        if (lane == 0 && v.tgt_n > 0) {
+            int n = v.tgt_n < v.scan_size ? v.tgt_n : v.scan_size;
+            int last = base_class(v.rc ? v.tgt[v.tgt_n - 1] : v.tgt[0]);
+            for (int i = 1; i < n; i++) {
+                int cur = base_class(v.rc ? v.tgt[v.tgt_n - 1 - i] : v.tgt[i]);
+                if (cur == 0) { if (last != 0) { r++; last = 0; } }
+                else { if (last != 1) { r++; last = cur; } }
+            }
+        }
+        runs = __shfl_sync(0xffffffffu, r, 0) + 1;
+    }
+
+    if (mine) {
+        const int G = v.rc ? B_C : B_G, Cc = v.rc ? B_G : B_C, A = v.rc ? B_T : B_A;
+        st.eg = slot[SLOT_EXT_MONO + G]; st.ec = slot[SLOT_EXT_MONO + Cc]; st.ea = slot[SLOT_EXT_MONO + A];
+        st.lg = slot[SLOT_LIG_MONO + G]; st.lc = slot[SLOT_LIG_MONO + Cc]; st.la = slot[SLOT_LIG_MONO + A];
+        st.tg = slot[SLOT_INS_MONO + G]; st.tc = slot[SLOT_INS_MONO + Cc]; st.ta = slot[SLOT_INS_MONO + A];
+        st.runs = runs; st.ext_len = v.ext_len; st.lig_len = v.lig_len; st.scan_size = v.scan_size;
+        st.jcode = jcode; st.ext_copy = v.ext_copy; st.lig_copy = v.lig_copy;
+        st.state = invalid ? 1 : 2;
+    }
+
+    // ---- the 192-double feature row ----
+    if (xrow) {
+#pragma unroll
+        for (int m = 0; m < 6; m++) {
+            uint32_t d = fd[m];
+            uint32_t kind = d & 7, part = (d >> 3) & 3, km1 = (d >> 5) & 3, j = (d >> 23) & 255;
+            int len = part == 0 ? v.ext_len : (part == 1 ? v.scan_size : v.lig_len);
+            double val;
+            if (invalid) val = 0.0;  // SVMipv4.cpp:63-68: 192 zeros
+            else if (kind == FK_RATIO) {
+                int s = v.rc ? (int)((d >> 15) & 255) : (int)((d >> 7) & 255);
+                val = __ddiv_rn((double)slot[s], (double)(len - (int)km1));
+            } else if (kind == FK_LEN) val = (double)len;
+            else if (kind == FK_LRC) val = v.lrc ? v.lrc[j] : 0.0;
+            else if (kind == FK_JUNC) val = (jcode == (int)j) ? 1.0 : 0.0;
+            else val = log_copy(j == 0 ? v.ext_copy : v.lig_copy, logtab);
+            xrow[lane + 32 * m] = val;
+        }
+    }
+    __syncwarp();
+}
+
+// The logistic model, one thread per candidate (SVMipv4.cpp:142-247).
+__device__ __forceinline__ double logistic_score(const Stash &s, const double *__restrict__ logtab)
+{
+    if (s.state == 0) return __longlong_as_double(0x7ff8000000000000LL);
+    if (s.state == 1) return -1000.0;
+    double v[MG_LOGIT_NVARS];
+    const double ext_length = (double)s.ext_len, lig_length = (double)s.lig_len, scan = (double)s.scan_size;
+    v[MG_V_BASES_PER_SWITCH] = __ddiv_rn(scan, (double)s.runs);
+    v[MG_V_EXT_LENGTH] = ext_length;
+    v[MG_V_LIG_LENGTH] = lig_length;
+    v[MG_V_TARGET_LENGTH] = s.scan_size > 250 ? 250.0 : scan;
+    v[MG_V_EXT_GC_CONTENT] = __ddiv_rn((double)(s.ec + s.eg), ext_length);
+    v[MG_V_LIG_GC_CONTENT] = __ddiv_rn((double)(s.lc + s.lg), lig_length);
+    v[MG_V_TARGET_GC_CONTENT] = __ddiv_rn((double)(s.tc + s.tg), scan);
+    v[MG_V_EXT_G_CONTENT] = __ddiv_rn((double)s.eg, ext_length);
+    v[MG_V_LIG_G_CONTENT] = __ddiv_rn((double)s.lg, lig_length);
+    v[MG_V_TARGET_G_CONTENT] = __ddiv_rn((double)s.tg, scan);
+    v[MG_V_EXT_A_CONTENT] = __ddiv_rn((double)s.ea, ext_length);
+    v[MG_V_LIG_A_CONTENT] = __ddiv_rn((double)s.la, lig_length);
+    v[MG_V_TARGET_A_CONTENT] = __ddiv_rn((double)s.ta, scan);
+    // junction_scores (SVMipv4.cpp:249-267, data); unknown key -> 0.0 (:171)
+    const double JT[16] = {0.0, 0.35, 0.046, 0.079, 0.34, 0.22, 0.55, -0.071,
+                           0.35, 0.92, 0.24, 0.48, -0.46, -0.35, -0.25, -0.98};
+    double js = 0.0;
+#pragma unroll
+    for (int i = 0; i < 16; i++) js = (s.jcode == i) ? JT[i] : js;
+    v[MG_V_JUNCTION_SCORE] = js;
+    v[MG_V_LOG_EXT_COPY] = log_copy(s.ext_copy, logtab);
+    v[MG_V_LOG_LIG_COPY] = log_copy(s.lig_copy, logtab);
+
+    double ex = __dsub_rn(MG_LOGIT_C0, (double)MG_LOGIT_C1);
+#define LIN(c, a, b) __dmul_rn((c), v[a])
+#define PROD(c, a, b) __dmul_rn(__dmul_rn((c), v[a]), v[b])
+#define SQ(c, a, b) __dmul_rn((c), __dmul_rn(v[a], v[a]))
+#define X(c, kind, a, b) ex = __dadd_rn(ex, kind(c, a, b));
+    MG_LOGIT_TERMS(X)
+#undef X
+#undef LIN
+#undef PROD
+#undef SQ
+    double p = pow(2.71828, ex);  // the literal 2.71828, not e (SVMipv4.cpp:247)
+    return __ddiv_rn(p, __dadd_rn(1.0, p));
+}
+
+// ------------------------------- grid front-end -------------------------------
+__device__ __forceinline__ int copy_lookup(const DevConfig *__restrict__ cfg, const DevRegion &r,
+                                           const int *__restrict__ copies, int start, int len)
+{
+    if (r.copy_off < 0) return 1;
+    for (int k = 0; k < cfg->n_oligo; k++)
+        if (cfg->oligo_sizes[k] == len) {
+            int i = start - r.seq_start;
+            if (i < 0 || i >= r.seq_len) return 0;
+            return copies[r.copy_off + (int64_t)k * r.seq_len + i];
+        }
+    return 0;  // absent key: map::operator[] yields 0 (mipgen.cpp:612-613)
+}
+
+__global__ void __launch_bounds__(kWarpsPerBlock * 32)
+k_feat_grid(const DevConfig *__restrict__ cfg, const DevRegion *__restrict__ regions, int n_regions,
+            const uint8_t *__restrict__ codes, const double *__restrict__ lrc_all, const int *__restrict__ copies,
+            const uint32_t *__restrict__ fdesc, const double *__restrict__ logtab, int64_t g0, int64_t g1,
+            uint8_t *__restrict__ valid, double *__restrict__ logistic, double *__restrict__ x)
+{
+    __shared__ int smem[kWarpsPerBlock * kWarpSmemInts];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    int *sm = smem + warp * kWarpSmemInts;
+    uint32_t fd[6];
+#pragma unroll
+    for (int m = 0; m < 6; m++) fd[m] = fdesc[lane + 32 * m];
+
+    const int n_pairs = cfg->n_pairs, n_cap = cfg->n_cap, inc = cfg->inc;
+    const int64_t per_scan = (int64_t)n_cap * n_pairs * 2;
+    const int64_t n_blocks = (g1 - g0 + 31) >> 5;
+    int ri = 0;
+    DevRegion r = regions[0];
+    int64_t r_end = (n_regions > 1) ? regions[1].grid_off : INT64_MAX;
+
+    for (int64_t blk = (int64_t)blockIdx.x * kWarpsPerBlock + warp; blk < n_blocks; blk += (int64_t)gridDim.x * kWarpsPerBlock) {
+        Stash st;
+        st.state = 0;
+        const int64_t gb = g0 + (blk << 5);
+        for (int c = 0; c < 32; c++) {
+            const int64_t g = gb + c;
+            if (g >= g1) break;
+            if (g < r.grid_off || g >= r_end) {  // find the region of g (uniform binary search)
+                int lo = 0, hi = n_regions - 1;
+                while (lo < hi) {
+                    int mid = (lo + hi + 1) >> 1;
+                    if (regions[mid].grid_off <= g) lo = mid; else hi = mid - 1;
+                }
+                ri = lo;
+                r = regions[ri];
+                r_end = (ri + 1 < n_regions) ? regions[ri + 1].grid_off : INT64_MAX;
+            }
+            const int64_t local = g - r.grid_off;
+            const int si = (int)(local / per_scan);
+            int rem = (int)(local - (int64_t)si * per_scan);
+            const int strand = rem & 1;
+            rem >>= 1;
+            const int ci = rem / n_pairs, p = rem - ci * n_pairs;
+            const int s = r.first_scan + si, cap = cfg->max_capture - ci * inc;
+            const int e = cfg->ext_len[p], l = cfg->lig_len[p];
+            // static skips: mipgen.cpp:429, 443, 444
+            bool ok = !(cap > r.stop_flanked - r.start_flanked + cfg->max_mip_overlap && cap - inc >= cfg->min_capture);
+            ok = ok && !(s - e <= 0 || s - l <= 0);
+            ok = ok && !(s + cap - e - 1 > r.seq_stop || s + cap - l - 1 > r.seq_stop);
+            const int t = s + cap - (e + l) - 1;  // scan_stop (:449)
+            View v;
+            v.rc = strand;
+            v.ext_len = e; v.lig_len = l; v.scan_size = t - s + 1;
+            const int ext_start = strand ? t + 1 : s - e;   // Plus/MinusSVMipv4 ctors
+            const int lig_start = strand ? s - l : t + 1;
+            const int eo = ext_start - r.seq_start, lo_ = lig_start - r.seq_start, to = s - r.seq_start;
+            // std::string::substr(off,len) throws for off > size; it clamps the length otherwise
+            ok = ok && eo >= 0 && lo_ >= 0 && to >= 0 && eo <= r.seq_len && lo_ <= r.seq_len && to <= r.seq_len && v.scan_size >= 0;
+            v.ok = ok;
+            const uint8_t *base = codes + r.seq_off;
+            v.ext = base + eo; v.lig = base + lo_; v.tgt = base + to;
+            v.ext_n = min(e, r.seq_len - eo); v.lig_n = min(l, r.seq_len - lo_); v.tgt_n = min(v.scan_size, r.seq_len - to);
+            v.ext_copy = 1; v.lig_copy = 1;
+            if (ok && r.copy_off >= 0) {
+                v.ext_copy = copy_lookup(cfg, r, copies, ext_start, e);
+                v.lig_copy = copy_lookup(cfg, r, copies, lig_start, l);
+            }
+            v.lrc = lrc_all ? lrc_all + (int64_t)ri * MG_NLRC : nullptr;
+            warp_candidate(v, sm, lane, fd, logtab, x ? x + (g - g0) * MG_NFEAT : nullptr, st, lane == c);
+        }
+        const int64_t g = gb + lane;
+        if (g < g1) {
+            if (valid) valid[g] = st.state != 0;
+            if (logistic) logistic[g] = logistic_score(st, logtab);
+        }
+    }
+}
+
+// ------------------------------ explicit front-end ------------------------------
+__global__ void __launch_bounds__(kWarpsPerBlock * 32)
+k_feat_explicit(const DevCand *__restrict__ cands, const uint8_t *__restrict__ codes, const double *__restrict__ lrc,
+                const uint32_t *__restrict__ fdesc, const double *__restrict__ logtab, int64_t n,
+                double *__restrict__ logistic, double *__restrict__ x)
+{
+    __shared__ int smem[kWarpsPerBlock * kWarpSmemInts];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    int *sm = smem + warp * kWarpSmemInts;
+    uint32_t fd[6];
+#pragma unroll
+    for (int m = 0; m < 6; m++) fd[m] = fdesc[lane + 32 * m];
+    const int64_t n_blocks = (n + 31) >> 5;
+    for (int64_t blk = (int64_t)blockIdx.x * kWarpsPerBlock + warp; blk < n_blocks; blk += (int64_t)gridDim.x * kWarpsPerBlock) {
+        Stash st;
+        st.state = 0;
+        for (int c = 0; c < 32; c++) {
+            const int64_t i = (blk << 5) + c;
+            if (i >= n) break;
+            const DevCand dc = cands[i];
+            View v;
+            v.ext = codes + dc.ext_off; v.lig = codes + dc.lig_off; v.tgt = codes + dc.tgt_off;
+            v.ext_n = dc.ext_n; v.lig_n = dc.lig_n; v.tgt_n = dc.tgt_n;
+            v.ext_len = dc.ext_len; v.lig_len = dc.lig_len; v.scan_size = dc.scan_size;
+            v.rc = 0; v.ext_copy = dc.ext_copy; v.lig_copy = dc.lig_copy;
+            v.lrc = lrc ? lrc + i * MG_NLRC : nullptr;
+            v.ok = 1;
+            warp_candidate(v, sm, lane, fd, logtab, x ? x + i * MG_NFEAT : nullptr, st, lane == c);
+        }
+        const int64_t i = (blk << 5) + lane;
+        if (i < n && logistic) logistic[i] = logistic_score(st, logtab);
+    }
+}
+
+// ---------------------------------- K-encode ----------------------------------
+__global__ void k_encode(const char *__restrict__ in, uint8_t *__restrict__ out, int64_t n)
+{
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        char ch = in[i];
+        uint8_t c = B_OTHER;
+        switch (ch) {
+        case 'A': c = B_A; break;
+        case 'C': c = B_C; break;
+        case 'G': c = B_G; break;
+        case 'T': c = B_T; break;
+        case 'N': c = B_N; break;
+        case '-': c = B_DASH; break;
+        default: break;
+        }
+        out[i] = c;
+    }
+}
+
+// ----------------------------------- K-lrc ------------------------------------
+// Featurev5::get_long_range_content (Featurev5.cpp:18-56): for each of the 44 k-mers of
+// mipgen.cpp:32, (count(mer) + count(revcomp) unless palindromic) / denom.
+__constant__ uint8_t c_lrc_k[MG_NLRC];
+__constant__ uint8_t c_lrc_code[MG_NLRC];
+
+__global__ void __launch_bounds__(256) k_lrc(const uint8_t *__restrict__ codes, int n, int denom, double *__restrict__ out)
+{
+    __shared__ int h[84];  // tri[64] di[16] mono[4]
+    if (threadIdx.x < 84) h[threadIdx.x] = 0;
+    __syncthreads();
+    for (int p = threadIdx.x; p < n; p += blockDim.x) {
+        uint32_t c0 = codes[p];
+        if (c0 >= 4) continue;
+        atomicAdd(&h[80 + c0], 1);
+        uint32_t c1 = p + 1 < n ? codes[p + 1] : B_NONE;
+        if (c1 >= 4) continue;
+        atomicAdd(&h[64 + c0 * 4 + c1], 1);
+        uint32_t c2 = p + 2 < n ? codes[p + 2] : B_NONE;
+        if (c2 >= 4) continue;
+        atomicAdd(&h[c0 * 16 + c1 * 4 + c2], 1);
+    }
+    __syncthreads();
+    if (threadIdx.x < MG_NLRC) {
+        int k = c_lrc_k[threadIdx.x], code = c_lrc_code[threadIdx.x];
+        int rc = 0;
+        for (int i = 0, q = code; i < k; i++, q >>= 2) rc = (rc << 2) | (3 - (q & 3));
+        int base = k == 3 ? 0 : (k == 2 ? 64 : 80);
+        double f = (double)h[base + code];
+        double v = (rc != code) ? __dadd_rn(f, (double)h[base + rc]) : f;
+        out[threadIdx.x] = __ddiv_rn(v, (double)denom);
+    }
+}
+
+}  // namespace
+
+// ------------------------------------ launchers ------------------------------------
+static int feat_grid_dim(mg_ctx *ctx, int64_t n)
+{
+    int64_t blocks = (n + 32 * kWarpsPerBlock - 1) / (32 * kWarpsPerBlock);
+    int64_t cap = (int64_t)ctx->sm_count * 8;  // 8 resident CTAs of 256 threads per SM
+    return (int)(blocks < cap ? (blocks > 0 ? blocks : 1) : cap);
+}
+
+int launch_encode(mg_ctx *ctx, const char *d_ascii, uint8_t *d_codes, int64_t n)
+{
+    if (n <= 0) return MG_OK;
+    int blocks = (int)((n + 255) / 256 < ctx->sm_count * 8 ? (n + 255) / 256 : ctx->sm_count * 8);
+    mg_time_begin(ctx, TM_OTHER, n);
+    k_encode<<<blocks, 256, 0, ctx->stream>>>(d_ascii, d_codes, n);
+    mg_time_end(ctx);
+    CUDA_TRY(ctx, cudaGetLastError());
+    return MG_OK;
+}
+
+int mg_upload_lrc_tables(mg_ctx *ctx, const uint8_t *k, const uint8_t *code)
+{
+    CUDA_TRY(ctx, cudaMemcpyToSymbol(c_lrc_k, k, MG_NLRC));
+    CUDA_TRY(ctx, cudaMemcpyToSymbol(c_lrc_code, code, MG_NLRC));
+    return MG_OK;
+}
+
+int launch_lrc(mg_ctx *ctx, const uint8_t *d_codes, int n, int denom, double *d_out44)
+{
+    mg_time_begin(ctx, TM_OTHER, n);
+    k_lrc<<<1, 256, 0, ctx->stream>>>(d_codes, n, denom, d_out44);
+    mg_time_end(ctx);
+    CUDA_TRY(ctx, cudaGetLastError());
+    return MG_OK;
+}
+
+int launch_feat_grid(mg_ctx *ctx, const mg_panel *p, int64_t g0, int64_t g1, uint8_t *d_valid, double *d_logistic,
+                     double *d_x)
+{
+    if (g1 <= g0) return MG_OK;
+    mg_time_begin(ctx, TM_FEAT, g1 - g0);
+    k_feat_grid<<<feat_grid_dim(ctx, g1 - g0), kWarpsPerBlock * 32, 0, ctx->stream>>>(
+        ctx->d_cfg, p->d_regions, p->n_regions, p->d_codes, p->d_lrc, p->d_copies, ctx->d_fdesc, ctx->d_logcopy, g0, g1,
+        d_valid, d_logistic, d_x);
+    mg_time_end(ctx);
+    CUDA_TRY(ctx, cudaGetLastError());
+    return MG_OK;
+}
+
+int launch_feat_explicit(mg_ctx *ctx, const DevCand *d_cands, const uint8_t *d_codes, const double *d_lrc, int64_t n,
+                         double *d_logistic, double *d_x)
+{
+    if (n <= 0) return MG_OK;
+    mg_time_begin(ctx, TM_FEAT, n);
+    k_feat_explicit<<<feat_grid_dim(ctx, n), kWarpsPerBlock * 32, 0, ctx->stream>>>(d_cands, d_codes, d_lrc, ctx->d_fdesc,
+                                                                                   ctx->d_logcopy, n, d_logistic, d_x);
+    mg_time_end(ctx);
+    CUDA_TRY(ctx, cudaGetLastError());
+    return MG_OK;
+}

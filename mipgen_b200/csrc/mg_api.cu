@@ -1,0 +1,816 @@
+// mg_api.cu -- host side of the C-ABI declared in include/mipgen_b200.h.
+//
+// Owns device memory, the stream, the model upload and the launch sequence.  There is no
+// CPU implementation of any scoring step in this file (or anywhere in the library): if the
+// device is missing or a launch fails, the call returns MG_ERR_CUDA.
+#include <math.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <algorithm>
+#include <fstream>
+#include <sstream>
+
+#include "mg_common.cuh"
+
+static std::string g_create_err;
+
+// ---------------------------------------------------------------------------
+// timing
+// ---------------------------------------------------------------------------
+static cudaEvent_t ev_get(mg_ctx *ctx)
+{
+    if (!ctx->ev_free.empty()) {
+        cudaEvent_t e = ctx->ev_free.back();
+        ctx->ev_free.pop_back();
+        return e;
+    }
+    cudaEvent_t e;
+    cudaEventCreate(&e);
+    return e;
+}
+
+int mg_time_begin(mg_ctx *ctx, int which, long units)
+{
+    EventPair ep;
+    ep.a = ev_get(ctx);
+    ep.b = ev_get(ctx);
+    ep.which = which;
+    ep.units = units;
+    cudaEventRecord(ep.a, ctx->stream);
+    ctx->ev_pending.push_back(ep);
+    return MG_OK;
+}
+
+int mg_time_end(mg_ctx *ctx)
+{
+    cudaEventRecord(ctx->ev_pending.back().b, ctx->stream);
+    return MG_OK;
+}
+
+static void drain_timings(mg_ctx *ctx)
+{
+    for (auto &ep : ctx->ev_pending) {
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, ep.a, ep.b) == cudaSuccess) {
+            if (ep.which == TM_FEAT) { ctx->tm.ms_feat += ms; ctx->tm.launches_feat++; ctx->tm.candidates_feat += ep.units; }
+            else if (ep.which == TM_SVR) { ctx->tm.ms_svr += ms; ctx->tm.launches_svr++; ctx->tm.candidates_svr += ep.units; }
+            else { ctx->tm.ms_other += ms; ctx->tm.launches_other++; }
+        }
+        ctx->ev_free.push_back(ep.a);
+        ctx->ev_free.push_back(ep.b);
+    }
+    ctx->ev_pending.clear();
+}
+
+// ---------------------------------------------------------------------------
+// static tables
+// ---------------------------------------------------------------------------
+// mipgen.cpp:32 (data): the 44 strand-symmetric k-mers of long_range_content
+static const char *const kFeatureMers[MG_NLRC] = {
+    "A", "AA", "AAA", "AAC", "AAG", "AAT", "AC", "ACA", "ACC", "ACG", "AG", "AGA", "AGC", "AGG", "AGT",
+    "AT", "ATA", "ATC", "ATG", "CAG", "CG", "CGG", "G", "GAC", "GAG", "GC", "GCG", "GG", "GGC", "GGG",
+    "GTG", "TA", "TAA", "TAC", "TAG", "TC", "TCC", "TCG", "TG", "TGA", "TGC", "TGG", "TTC", "TTG"};
+
+static int base_code(char c) { return c == 'A' ? 0 : c == 'C' ? 1 : c == 'G' ? 2 : 3; }
+
+static int revcomp_code(int code, int k)
+{
+    int rc = 0;
+    for (int i = 0; i < k; i++, code >>= 2) rc = (rc << 2) | (3 - (code & 3));
+    return rc;
+}
+
+// Feature layout of get_parameters (SVMipv4.cpp:60-113): k-mers in trie pre-order
+// ("A","AA","AAA",...), a G+C fraction right before "T", then the raw length.
+static void emit_block(std::vector<uint32_t> &fd, int part, int depth, int slot_tri, int slot_di, int slot_mono, int slot_gc)
+{
+    for (int a = 0; a < 4; a++) {
+        if (a == 3) fd.push_back(fd_pack(FK_RATIO, part, 0, slot_gc, slot_gc, 0));
+        fd.push_back(fd_pack(FK_RATIO, part, 0, slot_mono + a, slot_mono + revcomp_code(a, 1), 0));
+        for (int b = 0; b < 4; b++) {
+            int di = a * 4 + b;
+            fd.push_back(fd_pack(FK_RATIO, part, 1, slot_di + di, slot_di + revcomp_code(di, 2), 0));
+            if (depth < 3) continue;
+            for (int c = 0; c < 4; c++) {
+                int tri = di * 4 + c;
+                fd.push_back(fd_pack(FK_RATIO, part, 2, slot_tri + tri, slot_tri + revcomp_code(tri, 3), 0));
+            }
+        }
+    }
+    fd.push_back(fd_pack(FK_LEN, part, 0, 0, 0, 0));
+}
+
+static std::vector<uint32_t> build_feature_descriptors()
+{
+    std::vector<uint32_t> fd;
+    emit_block(fd, 0, 2, 0, SLOT_EXT_DI, SLOT_EXT_MONO, SLOT_EXT_GC);                 // 1..22
+    for (int j = 0; j < MG_NLRC; j++) fd.push_back(fd_pack(FK_LRC, 0, 0, 0, 0, j));    // 23..66
+    emit_block(fd, 1, 3, SLOT_INS_TRI, SLOT_INS_DI, SLOT_INS_MONO, SLOT_INS_GC);      // 67..152
+    emit_block(fd, 2, 2, 0, SLOT_LIG_DI, SLOT_LIG_MONO, SLOT_LIG_GC);                 // 153..174
+    for (int j = 0; j < 16; j++) fd.push_back(fd_pack(FK_JUNC, 2, 0, 0, 0, j));        // 175..190
+    fd.push_back(fd_pack(FK_COPY, 0, 0, 0, 0, 0));                                     // 191
+    fd.push_back(fd_pack(FK_COPY, 2, 0, 0, 0, 1));                                     // 192
+    return fd;
+}
+
+// ---------------------------------------------------------------------------
+// context
+// ---------------------------------------------------------------------------
+extern "C" const char *mg_version(void) { return "mipgen_b200 0.1 (sm_100a)"; }
+
+extern "C" const char *mg_last_error(const mg_ctx *ctx) { return ctx ? ctx->err.c_str() : g_create_err.c_str(); }
+
+extern "C" int mg_create(int device, mg_ctx **out)
+{
+    if (!out) return MG_ERR_INVALID;
+    *out = nullptr;
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count <= 0) {
+        g_create_err = std::string("no CUDA device available: ") + (e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0") +
+                       " (this library has no CPU fallback)";
+        return MG_ERR_CUDA;
+    }
+    if (device < 0 || device >= count) { g_create_err = "device ordinal out of range"; return MG_ERR_INVALID; }
+    mg_ctx *ctx = new mg_ctx();
+    ctx->device = device;
+    auto fail = [&](const char *what, cudaError_t err) {
+        g_create_err = std::string(what) + ": " + cudaGetErrorString(err);
+        delete ctx;
+        return MG_ERR_CUDA;
+    };
+    if ((e = cudaSetDevice(device)) != cudaSuccess) return fail("cudaSetDevice", e);
+    cudaDeviceProp prop;
+    if ((e = cudaGetDeviceProperties(&prop, device)) != cudaSuccess) return fail("cudaGetDeviceProperties", e);
+    if (prop.major != 10) {
+        g_create_err = "device is not sm_100 (Blackwell B200); kernels are built for sm_100a only";
+        delete ctx;
+        return MG_ERR_CUDA;
+    }
+    ctx->sm_count = prop.multiProcessorCount;
+    if ((e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking)) != cudaSuccess) return fail("cudaStreamCreate", e);
+
+    std::vector<uint32_t> fd = build_feature_descriptors();
+    if (fd.size() != MG_NFEAT) { g_create_err = "internal: feature table size"; delete ctx; return MG_ERR_INVALID; }
+    if ((e = cudaMalloc(&ctx->d_fdesc, MG_NFEAT * sizeof(uint32_t))) != cudaSuccess) return fail("cudaMalloc", e);
+    cudaMemcpy(ctx->d_fdesc, fd.data(), MG_NFEAT * sizeof(uint32_t), cudaMemcpyHostToDevice);
+    // log10 of copy numbers 0..100 from the host libm, so features 191/192 are bit-identical to glibc
+    double logtab[102];
+    for (int i = 0; i <= 100; i++) logtab[i] = log10((double)i);
+    logtab[101] = 2.0;
+    if ((e = cudaMalloc(&ctx->d_logcopy, sizeof logtab)) != cudaSuccess) return fail("cudaMalloc", e);
+    cudaMemcpy(ctx->d_logcopy, logtab, sizeof logtab, cudaMemcpyHostToDevice);
+    if ((e = cudaMalloc(&ctx->d_cfg, sizeof(DevConfig))) != cudaSuccess) return fail("cudaMalloc", e);
+    uint8_t lk[MG_NLRC], lc[MG_NLRC];
+    for (int i = 0; i < MG_NLRC; i++) {
+        int k = (int)strlen(kFeatureMers[i]), code = 0;
+        for (int j = 0; j < k; j++) code = code * 4 + base_code(kFeatureMers[i][j]);
+        lk[i] = (uint8_t)k;
+        lc[i] = (uint8_t)code;
+    }
+    if (mg_upload_lrc_tables(ctx, lk, lc) != MG_OK || launch_svr_setup(ctx) != MG_OK) {
+        g_create_err = ctx->err;
+        delete ctx;
+        return MG_ERR_CUDA;
+    }
+    *out = ctx;
+    return MG_OK;
+}
+
+static void free_model(mg_ctx *ctx)
+{
+    cudaFree(ctx->d_sv); cudaFree(ctx->d_ss); cudaFree(ctx->d_alpha);
+    ctx->d_sv = ctx->d_ss = ctx->d_alpha = nullptr;
+    ctx->has_model = false;
+}
+
+extern "C" void mg_destroy(mg_ctx *ctx)
+{
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    drain_timings(ctx);
+    for (auto e : ctx->ev_free) cudaEventDestroy(e);
+    if (ctx->sw_a) { cudaEventDestroy(ctx->sw_a); cudaEventDestroy(ctx->sw_b); }
+    free_model(ctx);
+    cudaFree(ctx->d_x); cudaFree(ctx->d_fdesc); cudaFree(ctx->d_logcopy); cudaFree(ctx->d_cfg);
+    cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+
+extern "C" int mg_sync(mg_ctx *ctx)
+{
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    return MG_OK;
+}
+
+extern "C" int mg_timer_start(mg_ctx *ctx)
+{
+    if (!ctx) return MG_ERR_INVALID;
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    if (!ctx->sw_a) { CUDA_TRY(ctx, cudaEventCreate(&ctx->sw_a)); CUDA_TRY(ctx, cudaEventCreate(&ctx->sw_b)); }
+    CUDA_TRY(ctx, cudaEventRecord(ctx->sw_a, ctx->stream));
+    return MG_OK;
+}
+
+extern "C" int mg_timer_stop(mg_ctx *ctx, double *ms)
+{
+    if (!ctx || !ctx->sw_a) return MG_ERR_INVALID;
+    CUDA_TRY(ctx, cudaEventRecord(ctx->sw_b, ctx->stream));
+    CUDA_TRY(ctx, cudaEventSynchronize(ctx->sw_b));
+    float f = 0.f;
+    CUDA_TRY(ctx, cudaEventElapsedTime(&f, ctx->sw_a, ctx->sw_b));
+    if (ms) *ms = f;
+    return MG_OK;
+}
+
+extern "C" int mg_reset_timings(mg_ctx *ctx)
+{
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    drain_timings(ctx);
+    memset(&ctx->tm, 0, sizeof ctx->tm);
+    return MG_OK;
+}
+
+extern "C" int mg_get_timings(mg_ctx *ctx, mg_timings *out)
+{
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    drain_timings(ctx);
+    if (out) *out = ctx->tm;
+    return MG_OK;
+}
+
+static int host_config_from(const mg_config *c, HostConfig &h, std::string &err)
+{
+    if (!c) return MG_ERR_INVALID;
+    if (c->n_pairs <= 0 || c->n_pairs > MG_MAX_PAIRS || c->n_oligo_sizes > MG_MAX_OLIGO || c->n_oligo_sizes < 0 ||
+        c->max_capture < c->min_capture || c->min_capture <= 0 || !c->ext_len || !c->lig_len) {
+        err = "mg_config: bad capture range or arm pair count";
+        return MG_ERR_INVALID;
+    }
+    h.max_capture = c->max_capture;
+    h.min_capture = c->min_capture;
+    h.inc = c->capture_increment == 0 ? 1 : c->capture_increment;  // mipgen.cpp:274
+    if (h.inc < 0) { err = "mg_config: negative capture_increment"; return MG_ERR_INVALID; }
+    h.max_mip_overlap = c->max_mip_overlap;
+    h.ext_len.assign(c->ext_len, c->ext_len + c->n_pairs);
+    h.lig_len.assign(c->lig_len, c->lig_len + c->n_pairs);
+    h.oligo_sizes.clear();
+    if (c->n_oligo_sizes > 0) h.oligo_sizes.assign(c->oligo_sizes, c->oligo_sizes + c->n_oligo_sizes);
+    h.n_cap = (h.max_capture - h.min_capture) / h.inc + 1;
+    h.max_sum = 0;
+    h.min_sum = 1 << 30;
+    for (int i = 0; i < c->n_pairs; i++) {
+        int s = h.ext_len[i] + h.lig_len[i];
+        if (h.ext_len[i] <= 0 || h.lig_len[i] <= 0 || s >= h.min_capture) {
+            err = "mg_config: arm lengths must be positive and sum below min_capture";
+            return MG_ERR_INVALID;
+        }
+        h.max_sum = std::max(h.max_sum, s);
+        h.min_sum = std::min(h.min_sum, s);
+    }
+    return MG_OK;
+}
+
+extern "C" int mg_set_config(mg_ctx *ctx, const mg_config *c)
+{
+    if (!ctx || !c) return MG_ERR_INVALID;
+    HostConfig h;
+    int hrc = host_config_from(c, h, ctx->err);
+    if (hrc != MG_OK) return hrc;
+    DevConfig *d = new DevConfig();
+    memset(d, 0, sizeof *d);
+    d->max_capture = h.max_capture; d->min_capture = h.min_capture; d->inc = h.inc; d->max_mip_overlap = h.max_mip_overlap;
+    d->n_cap = h.n_cap; d->n_pairs = c->n_pairs; d->max_sum = h.max_sum; d->min_sum = h.min_sum;
+    d->n_oligo = (int)h.oligo_sizes.size();
+    for (int i = 0; i < c->n_pairs; i++) { d->ext_len[i] = h.ext_len[i]; d->lig_len[i] = h.lig_len[i]; }
+    for (size_t i = 0; i < h.oligo_sizes.size(); i++) d->oligo_sizes[i] = h.oligo_sizes[i];
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    cudaError_t e = cudaMemcpy(ctx->d_cfg, d, sizeof *d, cudaMemcpyHostToDevice);
+    delete d;
+    if (e != cudaSuccess) { ctx->err = std::string("config upload: ") + cudaGetErrorString(e); return MG_ERR_CUDA; }
+    ctx->cfg = h;
+    ctx->has_cfg = true;
+    return MG_OK;
+}
+
+// ---------------------------------------------------------------------------
+// model
+// ---------------------------------------------------------------------------
+static int upload_model(mg_ctx *ctx, const std::vector<double> &dense, const std::vector<double> &tail, const std::vector<double> &alpha,
+                        int n_sv, double gamma, double rho)
+{
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    free_model(ctx);
+    int pad = std::max(SVR_BN, (n_sv + SVR_BN - 1) / SVR_BN * SVR_BN);
+    std::vector<double> sv((size_t)pad * MG_NFEAT, 0.0), ss(pad, 0.0), al(pad, 0.0);
+    for (int i = 0; i < n_sv; i++) {
+        double s = 0.0;
+        for (int k = 0; k < MG_NFEAT; k++) {
+            double v = dense[(size_t)i * MG_NFEAT + k];
+            sv[(size_t)i * MG_NFEAT + k] = v;
+            s += v * v;
+        }
+        ss[i] = s + tail[i];
+        al[i] = alpha[i];
+    }
+    CUDA_TRY(ctx, cudaMalloc(&ctx->d_sv, sv.size() * 8));
+    CUDA_TRY(ctx, cudaMalloc(&ctx->d_ss, ss.size() * 8));
+    CUDA_TRY(ctx, cudaMalloc(&ctx->d_alpha, al.size() * 8));
+    CUDA_TRY(ctx, cudaMemcpy(ctx->d_sv, sv.data(), sv.size() * 8, cudaMemcpyHostToDevice));
+    CUDA_TRY(ctx, cudaMemcpy(ctx->d_ss, ss.data(), ss.size() * 8, cudaMemcpyHostToDevice));
+    CUDA_TRY(ctx, cudaMemcpy(ctx->d_alpha, al.data(), al.size() * 8, cudaMemcpyHostToDevice));
+    ctx->n_sv = n_sv; ctx->n_sv_pad = pad; ctx->gamma = gamma; ctx->rho = rho;
+    ctx->has_model = true;
+    return MG_OK;
+}
+
+extern "C" int mg_set_svr_model(mg_ctx *ctx, const double *sv, const double *alpha, int n_sv, int n_feat, double gamma, double rho)
+{
+    if (!ctx || !sv || !alpha || n_sv < 0 || n_feat <= 0 || n_feat > MG_NFEAT) return MG_ERR_INVALID;
+    std::vector<double> dense((size_t)std::max(n_sv, 1) * MG_NFEAT, 0.0), tail(std::max(n_sv, 1), 0.0), al(alpha, alpha + n_sv);
+    for (int i = 0; i < n_sv; i++)
+        for (int k = 0; k < n_feat; k++) dense[(size_t)i * MG_NFEAT + k] = sv[(size_t)i * n_feat + k];
+    return upload_model(ctx, dense, tail, al, n_sv, gamma, rho);
+}
+
+// libsvm text model (format written by svm_save_model, svm.cpp:2644-2736; read by
+// svm_load_model, svm.cpp:2759-2973): header "key value" lines up to "SV", then one
+// line per support vector: "<coef> idx:val idx:val ...", absent idx meaning 0.
+extern "C" int mg_load_svr_model(mg_ctx *ctx, const char *path)
+{
+    if (!ctx || !path) return MG_ERR_INVALID;
+    std::ifstream in(path, std::ios::binary);
+    if (!in) { ctx->err = std::string("cannot open model file ") + path; return MG_ERR_MODEL; }
+    std::string line, svm_type, kernel_type;
+    double gamma = 0, rho = 0;
+    int nr_class = 0, total_sv = -1;
+    bool in_sv = false;
+    while (std::getline(in, line)) {
+        std::istringstream is(line);
+        std::string key;
+        if (!(is >> key)) continue;
+        if (key == "SV") { in_sv = true; break; }
+        if (key == "svm_type") is >> svm_type;
+        else if (key == "kernel_type") is >> kernel_type;
+        else if (key == "gamma") { std::string v; is >> v; gamma = strtod(v.c_str(), nullptr); }
+        else if (key == "rho") { std::string v; is >> v; rho = strtod(v.c_str(), nullptr); }
+        else if (key == "nr_class") is >> nr_class;
+        else if (key == "total_sv") is >> total_sv;
+        else if (key == "degree" || key == "coef0" || key == "label" || key == "nr_sv" || key == "probA" || key == "probB") {}
+        else { ctx->err = "unknown text in model file: [" + key + "]"; return MG_ERR_MODEL; }
+    }
+    if (!in_sv || total_sv < 0) { ctx->err = "model file has no SV section / total_sv"; return MG_ERR_MODEL; }
+    if ((svm_type != "epsilon_svr" && svm_type != "nu_svr") || kernel_type != "rbf" || nr_class != 2) {
+        ctx->err = "model is not an RBF epsilon_svr/nu_svr (this path implements only what mipgen uses)";
+        return MG_ERR_MODEL;
+    }
+    std::vector<double> dense((size_t)std::max(total_sv, 1) * MG_NFEAT, 0.0), tail(std::max(total_sv, 1), 0.0), alpha(std::max(total_sv, 1), 0.0);
+    for (int i = 0; i < total_sv; i++) {
+        if (!std::getline(in, line)) { ctx->err = "model file truncated in the SV section"; return MG_ERR_MODEL; }
+        const char *p = line.c_str();
+        char *end;
+        alpha[i] = strtod(p, &end);
+        p = end;
+        for (;;) {
+            while (*p == ' ' || *p == '\t') p++;
+            if (*p == 0 || *p == '\n' || *p == '\r') break;
+            long idx = strtol(p, &end, 10);
+            if (end == p || *end != ':') break;
+            p = end + 1;
+            double val = strtod(p, &end);
+            if (end == p) break;
+            p = end;
+            if (idx >= 1 && idx <= MG_NFEAT) dense[(size_t)i * MG_NFEAT + (idx - 1)] = val;
+            else tail[i] += val * val;  // feature the 192-vector never carries: contributes s^2
+        }
+    }
+    alpha.resize(total_sv);
+    return upload_model(ctx, dense, tail, alpha, total_sv, gamma, rho);
+}
+
+extern "C" int mg_model_info(const mg_ctx *ctx, int *n_sv, double *gamma, double *rho)
+{
+    if (!ctx || !ctx->has_model) return MG_ERR_NOMODEL;
+    if (n_sv) *n_sv = ctx->n_sv;
+    if (gamma) *gamma = ctx->gamma;
+    if (rho) *rho = ctx->rho;
+    return MG_OK;
+}
+
+// ---------------------------------------------------------------------------
+// workspace
+// ---------------------------------------------------------------------------
+static const int64_t kMaxChunkRows = 1 << 21;  // 2 M candidates = 3.2 GB of feature rows in flight
+
+static int ensure_x(mg_ctx *ctx, int64_t rows)
+{
+    rows = (rows + SVR_BM - 1) / SVR_BM * SVR_BM;
+    if ((size_t)rows <= ctx->x_rows_cap) return MG_OK;
+    cudaStreamSynchronize(ctx->stream);
+    cudaFree(ctx->d_x);
+    ctx->d_x = nullptr;
+    ctx->x_rows_cap = 0;
+    CUDA_TRY(ctx, cudaMalloc(&ctx->d_x, (size_t)rows * MG_NFEAT * 8));
+    CUDA_TRY(ctx, cudaMemsetAsync(ctx->d_x, 0, (size_t)rows * MG_NFEAT * 8, ctx->stream));
+    ctx->x_rows_cap = (size_t)rows;
+    return MG_OK;
+}
+
+// ---------------------------------------------------------------------------
+// svm_predict on dense rows
+// ---------------------------------------------------------------------------
+static int predict_rows(mg_ctx *ctx, const double *x, long n, long ld, double *out, bool direct)
+{
+    if (!ctx || !x || !out || n < 0 || ld < MG_NFEAT) return MG_ERR_INVALID;
+    if (!ctx->has_model) { ctx->err = "no SVR model loaded"; return MG_ERR_NOMODEL; }
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    double *d_out = nullptr;
+    for (long i0 = 0; i0 < n; i0 += kMaxChunkRows) {
+        long m = std::min<long>(kMaxChunkRows, n - i0);
+        int rc = ensure_x(ctx, m);
+        if (rc != MG_OK) return rc;
+        if (!d_out) CUDA_TRY(ctx, cudaMalloc(&d_out, (size_t)std::min<long>(n, kMaxChunkRows) * 8));
+        CUDA_TRY(ctx, cudaMemcpy2DAsync(ctx->d_x, MG_NFEAT * 8, x + i0 * ld, (size_t)ld * 8, MG_NFEAT * 8, (size_t)m,
+                                         cudaMemcpyHostToDevice, ctx->stream));
+        rc = direct ? launch_svr_direct(ctx, ctx->d_x, m, MG_NFEAT, d_out) : launch_svr(ctx, ctx->d_x, m, nullptr, d_out);
+        if (rc != MG_OK) { cudaFree(d_out); return rc; }
+        CUDA_TRY(ctx, cudaMemcpyAsync(out + i0, d_out, (size_t)m * 8, cudaMemcpyDeviceToHost, ctx->stream));
+        CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    }
+    cudaFree(d_out);
+    return MG_OK;
+}
+
+extern "C" int mg_svr_predict(mg_ctx *ctx, const double *x, long n, long ld, double *out) { return predict_rows(ctx, x, n, ld, out, false); }
+extern "C" int mg_svr_predict_direct(mg_ctx *ctx, const double *x, long n, long ld, double *out) { return predict_rows(ctx, x, n, ld, out, true); }
+
+// ---------------------------------------------------------------------------
+// long-range content
+// ---------------------------------------------------------------------------
+extern "C" int mg_long_range_content(mg_ctx *ctx, const char *ext_seq, int n, int denom, double out[MG_NLRC])
+{
+    if (!ctx || !ext_seq || n < 0 || !out) return MG_ERR_INVALID;
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    char *d_a = nullptr;
+    uint8_t *d_c = nullptr;
+    double *d_o = nullptr;
+    CUDA_TRY(ctx, cudaMalloc(&d_a, std::max(n, 1)));
+    CUDA_TRY(ctx, cudaMalloc(&d_c, std::max(n, 1)));
+    CUDA_TRY(ctx, cudaMalloc(&d_o, MG_NLRC * 8));
+    CUDA_TRY(ctx, cudaMemcpyAsync(d_a, ext_seq, n, cudaMemcpyHostToDevice, ctx->stream));
+    int rc = launch_encode(ctx, d_a, d_c, n);
+    if (rc == MG_OK) rc = launch_lrc(ctx, d_c, n, denom, d_o);
+    if (rc == MG_OK) {
+        cudaError_t e = cudaMemcpyAsync(out, d_o, MG_NLRC * 8, cudaMemcpyDeviceToHost, ctx->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+        if (e != cudaSuccess) { ctx->err = cudaGetErrorString(e); rc = MG_ERR_CUDA; }
+    }
+    cudaFree(d_a); cudaFree(d_c); cudaFree(d_o);
+    return rc;
+}
+
+// ---------------------------------------------------------------------------
+// explicit candidates
+// ---------------------------------------------------------------------------
+extern "C" int mg_score_candidates(mg_ctx *ctx, const mg_candidate *cands, long n, const double *lrc, int want, double *logistic,
+                                   double *svr, double *features)
+{
+    if (!ctx || (!cands && n > 0) || n < 0) return MG_ERR_INVALID;
+    const bool w_log = (want & MG_WANT_LOGISTIC) && logistic, w_svr = (want & MG_WANT_SVR) && svr, w_feat = (want & MG_WANT_FEATURES) && features;
+    if (w_svr && !ctx->has_model) { ctx->err = "no SVR model loaded"; return MG_ERR_NOMODEL; }
+    if (n == 0) return MG_OK;
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    int rc = MG_OK;
+    for (long i0 = 0; i0 < n && rc == MG_OK; i0 += kMaxChunkRows) {
+        const long m = std::min<long>(kMaxChunkRows, n - i0);
+        std::vector<DevCand> dc(m);
+        size_t total = 0;
+        for (long i = 0; i < m; i++) {
+            const mg_candidate &c = cands[i0 + i];
+            if (c.ext_n < 0 || c.lig_n < 0 || c.tgt_n < 0 || (!c.ext && c.ext_n) || (!c.lig && c.lig_n) || (!c.tgt && c.tgt_n)) {
+                ctx->err = "mg_score_candidates: bad string in candidate";
+                return MG_ERR_INVALID;
+            }
+            total += (size_t)c.ext_n + c.lig_n + c.tgt_n;
+        }
+        std::vector<char> ascii(std::max<size_t>(total, 1));
+        size_t off = 0;
+        for (long i = 0; i < m; i++) {
+            const mg_candidate &c = cands[i0 + i];
+            DevCand &d = dc[i];
+            d.ext_off = (int64_t)off; memcpy(&ascii[off], c.ext, c.ext_n); off += c.ext_n;
+            d.lig_off = (int64_t)off; memcpy(&ascii[off], c.lig, c.lig_n); off += c.lig_n;
+            d.tgt_off = (int64_t)off; memcpy(&ascii[off], c.tgt, c.tgt_n); off += c.tgt_n;
+            d.ext_n = c.ext_n; d.lig_n = c.lig_n; d.tgt_n = c.tgt_n;
+            d.ext_len = c.ext_len; d.lig_len = c.lig_len; d.scan_size = c.scan_size;
+            d.ext_copy = c.ext_copy; d.lig_copy = c.lig_copy; d.pad = 0;
+        }
+        char *d_a = nullptr; uint8_t *d_c = nullptr; DevCand *d_dc = nullptr; double *d_lrc = nullptr, *d_log = nullptr, *d_svr = nullptr;
+        auto cleanup = [&]() { cudaFree(d_a); cudaFree(d_c); cudaFree(d_dc); cudaFree(d_lrc); cudaFree(d_log); cudaFree(d_svr); };
+#define TRY_FREE(expr) do { cudaError_t _e = (expr); if (_e != cudaSuccess) { ctx->err = std::string(#expr) + ": " + cudaGetErrorString(_e); cleanup(); return MG_ERR_CUDA; } } while (0)
+        TRY_FREE(cudaMalloc(&d_a, ascii.size()));
+        TRY_FREE(cudaMalloc(&d_c, ascii.size()));
+        TRY_FREE(cudaMalloc(&d_dc, (size_t)m * sizeof(DevCand)));
+        TRY_FREE(cudaMemcpyAsync(d_a, ascii.data(), ascii.size(), cudaMemcpyHostToDevice, ctx->stream));
+        TRY_FREE(cudaMemcpyAsync(d_dc, dc.data(), (size_t)m * sizeof(DevCand), cudaMemcpyHostToDevice, ctx->stream));
+        if (lrc) {
+            TRY_FREE(cudaMalloc(&d_lrc, (size_t)m * MG_NLRC * 8));
+            TRY_FREE(cudaMemcpyAsync(d_lrc, lrc + i0 * MG_NLRC, (size_t)m * MG_NLRC * 8, cudaMemcpyHostToDevice, ctx->stream));
+        }
+        if (w_log) TRY_FREE(cudaMalloc(&d_log, (size_t)m * 8));
+        if (w_svr) TRY_FREE(cudaMalloc(&d_svr, (size_t)m * 8));
+        const bool need_x = w_svr || w_feat;
+        if (need_x && (rc = ensure_x(ctx, m)) != MG_OK) { cleanup(); return rc; }
+        rc = launch_encode(ctx, d_a, d_c, (int64_t)ascii.size());
+        if (rc == MG_OK) rc = launch_feat_explicit(ctx, d_dc, d_c, d_lrc, m, d_log, need_x ? ctx->d_x : nullptr);
+        if (rc == MG_OK && w_svr) rc = launch_svr(ctx, ctx->d_x, m, nullptr, d_svr);
+        if (rc == MG_OK) {
+            if (w_log) TRY_FREE(cudaMemcpyAsync(logistic + i0, d_log, (size_t)m * 8, cudaMemcpyDeviceToHost, ctx->stream));
+            if (w_svr) TRY_FREE(cudaMemcpyAsync(svr + i0, d_svr, (size_t)m * 8, cudaMemcpyDeviceToHost, ctx->stream));
+            if (w_feat) TRY_FREE(cudaMemcpyAsync(features + i0 * MG_NFEAT, ctx->d_x, (size_t)m * MG_NFEAT * 8, cudaMemcpyDeviceToHost, ctx->stream));
+            TRY_FREE(cudaStreamSynchronize(ctx->stream));
+        }
+#undef TRY_FREE
+        cleanup();
+    }
+    return rc;
+}
+
+// ---------------------------------------------------------------------------
+// region grids
+// ---------------------------------------------------------------------------
+static int first_scan_start(const HostConfig &c, const mg_region *r)
+{
+    // mipgen.cpp:421-425 (the loop pre-increments)
+    int cur = r->start_flanked - c.max_capture + c.max_sum;
+    if (cur < 0) cur = 0;
+    return cur + 1;
+}
+
+static int n_scan(const HostConfig &c, const mg_region *r)
+{
+    int n = r->stop_flanked - first_scan_start(c, r) + 1;
+    return n < 0 ? 0 : n;
+}
+
+extern "C" int mg_first_scan_start(const mg_ctx *ctx, const mg_region *r) { return (ctx && ctx->has_cfg && r) ? first_scan_start(ctx->cfg, r) : 0; }
+
+extern "C" int64_t mg_grid_size(const mg_ctx *ctx, const mg_region *r)
+{
+    if (!ctx || !ctx->has_cfg || !r) return 0;
+    return (int64_t)n_scan(ctx->cfg, r) * ctx->cfg.n_cap * (int64_t)ctx->cfg.ext_len.size() * 2;
+}
+
+extern "C" int64_t mg_config_grid_size(const mg_config *cfg, const mg_region *r)
+{
+    HostConfig h;
+    std::string err;
+    if (!r || host_config_from(cfg, h, err) != MG_OK) return -1;
+    return (int64_t)n_scan(h, r) * h.n_cap * (int64_t)h.ext_len.size() * 2;
+}
+
+extern "C" int mg_config_first_scan_start(const mg_config *cfg, const mg_region *r)
+{
+    HostConfig h;
+    std::string err;
+    if (!r || host_config_from(cfg, h, err) != MG_OK) return -1;
+    return first_scan_start(h, r);
+}
+
+extern "C" void mg_panel_destroy(mg_panel *p)
+{
+    if (!p) return;
+    cudaSetDevice(p->ctx->device);
+    cudaStreamSynchronize(p->ctx->stream);
+    cudaFree(p->d_regions); cudaFree(p->d_codes); cudaFree(p->d_lrc); cudaFree(p->d_copies);
+    cudaFree(p->d_valid); cudaFree(p->d_logistic); cudaFree(p->d_svr); cudaFree(p->d_feat);
+    delete p;
+}
+
+extern "C" int mg_panel_create(mg_ctx *ctx, const mg_region *regions, int n, mg_panel **out)
+{
+    if (!ctx || !out || n < 0 || (!regions && n > 0)) return MG_ERR_INVALID;
+    *out = nullptr;
+    if (!ctx->has_cfg) { ctx->err = "mg_set_config has not been called"; return MG_ERR_NOCONFIG; }
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    mg_panel *p = new mg_panel();
+    p->ctx = ctx;
+    p->n_regions = n;
+    p->offsets.assign(n + 1, 0);
+    p->h_regions.resize(std::max(n, 1));
+    int64_t codes = 0, copies = 0;
+    bool any_lrc = false;
+    const int n_oligo = (int)ctx->cfg.oligo_sizes.size();
+    for (int i = 0; i < n; i++) {
+        const mg_region &r = regions[i];
+        if (!r.seq || r.seq_len <= 0 || r.seq_len != r.seq_stop - r.seq_start + 1 || r.stop_flanked < r.start_flanked) {
+            ctx->err = "mg_panel_create: region " + std::to_string(i) + " has inconsistent sequence coordinates";
+            delete p;
+            return MG_ERR_INVALID;
+        }
+        if (r.copies && n_oligo == 0) {
+            ctx->err = "mg_panel_create: copy table given but the config has no oligo_sizes";
+            delete p;
+            return MG_ERR_INVALID;
+        }
+        DevRegion &d = p->h_regions[i];
+        d.seq_off = codes; d.grid_off = p->offsets[i];
+        d.copy_off = r.copies ? copies : -1;
+        d.seq_len = r.seq_len; d.seq_start = r.seq_start; d.seq_stop = r.seq_stop;
+        d.start_flanked = r.start_flanked; d.stop_flanked = r.stop_flanked;
+        d.first_scan = first_scan_start(ctx->cfg, &r); d.n_scan = n_scan(ctx->cfg, &r); d.pad = 0;
+        codes += r.seq_len;
+        if (r.copies) copies += (int64_t)n_oligo * r.seq_len;
+        any_lrc |= r.lrc != nullptr;
+        p->offsets[i + 1] = p->offsets[i] + mg_grid_size(ctx, &r);
+    }
+    p->n_cand = p->offsets[n];
+    p->n_codes = codes;
+#define P_TRY(expr) do { cudaError_t _e = (expr); if (_e != cudaSuccess) { ctx->err = std::string(#expr) + ": " + cudaGetErrorString(_e); mg_panel_destroy(p); return MG_ERR_CUDA; } } while (0)
+    if (n > 0) {
+        std::vector<char> ascii((size_t)codes);
+        std::vector<double> lrc(any_lrc ? (size_t)n * MG_NLRC : 0, 0.0);
+        std::vector<int> cp((size_t)copies);
+        for (int i = 0; i < n; i++) {
+            const mg_region &r = regions[i];
+            memcpy(&ascii[p->h_regions[i].seq_off], r.seq, r.seq_len);
+            if (r.lrc) memcpy(&lrc[(size_t)i * MG_NLRC], r.lrc, MG_NLRC * 8);
+            if (r.copies) memcpy(&cp[p->h_regions[i].copy_off], r.copies, (size_t)n_oligo * r.seq_len * sizeof(int));
+        }
+        char *d_ascii = nullptr;
+        P_TRY(cudaMalloc(&d_ascii, (size_t)codes));
+        P_TRY(cudaMalloc(&p->d_codes, (size_t)codes));
+        P_TRY(cudaMalloc(&p->d_regions, (size_t)n * sizeof(DevRegion)));
+        P_TRY(cudaMemcpyAsync(d_ascii, ascii.data(), (size_t)codes, cudaMemcpyHostToDevice, ctx->stream));
+        P_TRY(cudaMemcpyAsync(p->d_regions, p->h_regions.data(), (size_t)n * sizeof(DevRegion), cudaMemcpyHostToDevice, ctx->stream));
+        if (any_lrc) {
+            P_TRY(cudaMalloc(&p->d_lrc, lrc.size() * 8));
+            P_TRY(cudaMemcpyAsync(p->d_lrc, lrc.data(), lrc.size() * 8, cudaMemcpyHostToDevice, ctx->stream));
+        }
+        if (copies > 0) {
+            P_TRY(cudaMalloc(&p->d_copies, (size_t)copies * sizeof(int)));
+            P_TRY(cudaMemcpyAsync(p->d_copies, cp.data(), (size_t)copies * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+        }
+        int rc = launch_encode(ctx, d_ascii, p->d_codes, codes);
+        cudaStreamSynchronize(ctx->stream);  // host staging vectors go out of scope
+        cudaFree(d_ascii);
+        if (rc != MG_OK) { mg_panel_destroy(p); return rc; }
+    }
+    if (p->n_cand > 0) {
+        P_TRY(cudaMalloc(&p->d_valid, (size_t)p->n_cand));
+        P_TRY(cudaMalloc(&p->d_logistic, (size_t)p->n_cand * 8));
+    }
+#undef P_TRY
+    *out = p;
+    return MG_OK;
+}
+
+extern "C" int64_t mg_panel_candidates(const mg_panel *p) { return p ? p->n_cand : 0; }
+
+extern "C" int mg_panel_score(mg_ctx *ctx, mg_panel *p, int want)
+{
+    if (!ctx || !p || p->ctx != ctx) return MG_ERR_INVALID;
+    if ((want & MG_WANT_SVR) && !ctx->has_model) { ctx->err = "no SVR model loaded"; return MG_ERR_NOMODEL; }
+    if (p->n_cand == 0) return MG_OK;
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    const bool w_log = want & MG_WANT_LOGISTIC, w_svr = want & MG_WANT_SVR, w_feat = want & MG_WANT_FEATURES;
+    if (w_svr && !p->d_svr) CUDA_TRY(ctx, cudaMalloc(&p->d_svr, (size_t)p->n_cand * 8));
+    if (w_feat && !p->d_feat) {
+        int64_t rows = (p->n_cand + SVR_BM - 1) / SVR_BM * SVR_BM;
+        CUDA_TRY(ctx, cudaMalloc(&p->d_feat, (size_t)rows * MG_NFEAT * 8));
+        CUDA_TRY(ctx, cudaMemsetAsync(p->d_feat, 0, (size_t)rows * MG_NFEAT * 8, ctx->stream));
+    }
+    int rc = MG_OK;
+    if (!w_svr && !w_feat) {
+        rc = launch_feat_grid(ctx, p, 0, p->n_cand, p->d_valid, w_log ? p->d_logistic : nullptr, nullptr);
+    } else if (w_feat) {
+        rc = launch_feat_grid(ctx, p, 0, p->n_cand, p->d_valid, w_log ? p->d_logistic : nullptr, p->d_feat);
+        if (rc == MG_OK && w_svr) rc = launch_svr(ctx, p->d_feat, p->n_cand, p->d_valid, p->d_svr);
+    } else {
+        const int64_t chunk = std::min<int64_t>(kMaxChunkRows, p->n_cand);
+        if ((rc = ensure_x(ctx, chunk)) != MG_OK) return rc;
+        for (int64_t g0 = 0; g0 < p->n_cand && rc == MG_OK; g0 += chunk) {
+            const int64_t g1 = std::min(p->n_cand, g0 + chunk);
+            rc = launch_feat_grid(ctx, p, g0, g1, p->d_valid, w_log ? p->d_logistic : nullptr, ctx->d_x);
+            if (rc == MG_OK) rc = launch_svr(ctx, ctx->d_x, g1 - g0, p->d_valid + g0, p->d_svr + g0);
+        }
+    }
+    if (rc == MG_OK) {
+        p->has_valid = true;
+        p->has_logistic |= w_log;
+        p->has_svr |= w_svr;
+        p->has_feat |= w_feat;
+    }
+    return rc;
+}
+
+extern "C" int mg_panel_fetch(mg_ctx *ctx, mg_panel *p, uint8_t *valid, double *logistic, double *svr, double *features)
+{
+    if (!ctx || !p || p->ctx != ctx) return MG_ERR_INVALID;
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    if (p->n_cand > 0) {
+        if ((valid && !p->has_valid) || (logistic && !p->has_logistic) || (svr && !p->has_svr) || (features && !p->has_feat)) {
+            ctx->err = "mg_panel_fetch: requested output was never computed";
+            return MG_ERR_INVALID;
+        }
+        if (valid) CUDA_TRY(ctx, cudaMemcpyAsync(valid, p->d_valid, (size_t)p->n_cand, cudaMemcpyDeviceToHost, ctx->stream));
+        if (logistic) CUDA_TRY(ctx, cudaMemcpyAsync(logistic, p->d_logistic, (size_t)p->n_cand * 8, cudaMemcpyDeviceToHost, ctx->stream));
+        if (svr) CUDA_TRY(ctx, cudaMemcpyAsync(svr, p->d_svr, (size_t)p->n_cand * 8, cudaMemcpyDeviceToHost, ctx->stream));
+        if (features) CUDA_TRY(ctx, cudaMemcpyAsync(features, p->d_feat, (size_t)p->n_cand * MG_NFEAT * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    }
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    return MG_OK;
+}
+
+extern "C" int mg_panel_device_ptrs(const mg_panel *p, const uint8_t **valid, const double **logistic, const double **svr)
+{
+    if (!p) return MG_ERR_INVALID;
+    if (valid) *valid = p->has_valid ? p->d_valid : nullptr;
+    if (logistic) *logistic = p->has_logistic ? p->d_logistic : nullptr;
+    if (svr) *svr = p->has_svr ? p->d_svr : nullptr;
+    return MG_OK;
+}
+
+extern "C" int64_t mg_panel_valid_candidates(const mg_panel *p)
+{
+    if (!p || !p->has_valid || p->n_cand == 0) return 0;
+    std::vector<uint8_t> v((size_t)p->n_cand);
+    cudaSetDevice(p->ctx->device);
+    cudaStreamSynchronize(p->ctx->stream);
+    if (cudaMemcpy(v.data(), p->d_valid, v.size(), cudaMemcpyDeviceToHost) != cudaSuccess) return -1;
+    int64_t c = 0;
+    for (uint8_t b : v) c += b;
+    return c;
+}
+
+extern "C" int mg_score_regions(mg_ctx *ctx, const mg_region *regions, int n, int want, int64_t *out_offsets, uint8_t *valid,
+                                double *logistic, double *svr, double *features)
+{
+    mg_panel *p = nullptr;
+    int rc = mg_panel_create(ctx, regions, n, &p);
+    if (rc != MG_OK) return rc;
+    if (out_offsets) memcpy(out_offsets, p->offsets.data(), (size_t)(n + 1) * sizeof(int64_t));
+    int w = 0;
+    if ((want & MG_WANT_LOGISTIC) && logistic) w |= MG_WANT_LOGISTIC;
+    if ((want & MG_WANT_SVR) && svr) w |= MG_WANT_SVR;
+    if ((want & MG_WANT_FEATURES) && features) w |= MG_WANT_FEATURES;
+    rc = mg_panel_score(ctx, p, w);
+    if (rc == MG_OK)
+        rc = mg_panel_fetch(ctx, p, valid, (w & MG_WANT_LOGISTIC) ? logistic : nullptr, (w & MG_WANT_SVR) ? svr : nullptr,
+                            (w & MG_WANT_FEATURES) ? features : nullptr);
+    mg_panel_destroy(p);
+    return rc;
+}
+
+// ---------------------------------------------------------------------------
+// host helper: the score-dependent control flow of the tile loop
+// ---------------------------------------------------------------------------
+extern "C" int64_t mg_tile_replay(const mg_config *cfg, const mg_region *r, const uint8_t *valid, const double *score, int method,
+                                  int heuristic, double upper, int64_t *out_idx, int64_t cap)
+{
+    HostConfig c;
+    std::string err;
+    if (!r || !valid || !score || host_config_from(cfg, c, err) != MG_OK) return -1;
+    const int n_pairs = (int)c.ext_len.size(), ns = n_scan(c, r);
+    // arm-sum groups: maximal runs of pairs with equal ext+lig (mipgen.cpp:431, 438)
+    std::vector<std::pair<int, int>> groups;
+    for (int p = 0; p < n_pairs;) {
+        int q = p, sum = c.ext_len[p] + c.lig_len[p];
+        while (q < n_pairs && c.ext_len[q] + c.lig_len[q] == sum) q++;
+        groups.emplace_back(p, q);
+        p = q;
+    }
+    int64_t n = 0;
+    for (int si = 0; si < ns; si++) {
+        double best = 0;  // previous_best_score, reset per scan start (:426)
+        for (int ci = 0; ci < c.n_cap; ci++) {
+            const int capture = c.max_capture - ci * c.inc;
+            if (capture > r->stop_flanked - r->start_flanked + c.max_mip_overlap && capture - c.inc >= c.min_capture) continue;  // :429
+            if (best > upper) continue;                                                                                        // :430
+            for (auto &g : groups) {
+                const int sum = c.ext_len[g.first] + c.lig_len[g.first];
+                if (best > upper && sum != c.min_sum) continue;  // :434
+                int prev_minus = 0, prev_plus = 0;               // ints in the reference (:435-436)
+                for (int k = g.first; k < g.second; k++) {
+                    const int64_t idx = (((int64_t)si * c.n_cap + ci) * n_pairs + k) * 2;
+                    if (!valid[idx]) continue;  // :443-444
+                    const double plus = score[idx], minus = score[idx + 1];
+                    if (out_idx && n + 2 <= cap) { out_idx[n] = idx; out_idx[n + 1] = idx + 1; }
+                    n += 2;
+                    best = minus > plus ? minus : plus;  // :495
+                    const bool stop = method == 0 && heuristic && plus < prev_plus && minus < prev_minus;  // :494
+                    prev_minus = (int)minus;  // :496
+                    prev_plus = (int)plus;    // :497
+                    if (stop) break;          // skip_ahead: the rest of this arm-sum list is skipped (:440)
+                }
+            }
+        }
+    }
+    return n;
+}

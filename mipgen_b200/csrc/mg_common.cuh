@@ -1,0 +1,184 @@
+// mg_common.cuh -- shared device/host definitions for the MIPgen B200 hot path.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <string>
+#include <vector>
+
+#include "../../include/mipgen_b200.h"
+
+// ---------------------------------------------------------------------------
+// base codes (one byte per base in HBM; the reference distinguishes more than
+// four symbols: 'N' invalidates an arm, '-' invalidates via mip_seq, every other
+// character simply never matches a k-mer -- SVMipv4.cpp:63,116; MinusSVMipv4.cpp:24-26)
+// ---------------------------------------------------------------------------
+enum : uint8_t { B_A = 0, B_C = 1, B_G = 2, B_T = 3, B_N = 4, B_DASH = 5, B_OTHER = 6, B_NONE = 7 };
+
+#define MG_MAX_PAIRS 1024
+#define MG_MAX_OLIGO 64
+
+// grid configuration as the kernels see it (lives in global memory, read uniformly)
+struct DevConfig {
+    int max_capture, min_capture, inc, max_mip_overlap;
+    int n_cap, n_pairs, max_sum, min_sum;
+    int n_oligo;
+    int ext_len[MG_MAX_PAIRS];
+    int lig_len[MG_MAX_PAIRS];
+    int oligo_sizes[MG_MAX_OLIGO];
+};
+
+// one region as the kernels see it
+struct DevRegion {
+    int64_t seq_off;    // offset of the region's codes in the panel's code array
+    int64_t grid_off;   // first global candidate index of the region's grid
+    int64_t copy_off;   // offset into the panel's copy array, or -1
+    int seq_len, seq_start, seq_stop;
+    int start_flanked, stop_flanked;
+    int first_scan, n_scan;
+    int pad;
+};
+
+// one explicit candidate (strand-oriented codes in a packed buffer)
+struct DevCand {
+    int64_t ext_off, lig_off, tgt_off;
+    int ext_n, lig_n, tgt_n;
+    int ext_len, lig_len, scan_size;
+    int ext_copy, lig_copy;
+    int pad;
+};
+
+// ---------------------------------------------------------------------------
+// feature descriptors: what each of the 192 outputs of get_parameters is
+// (SVMipv4.cpp:60-113)
+// ---------------------------------------------------------------------------
+enum : uint32_t {
+    FK_RATIO = 0,  // count slot / (len - k + 1)
+    FK_LEN = 1,    // raw arm / insert length
+    FK_LRC = 2,    // long_range_content[j]
+    FK_JUNC = 3,   // one-hot of the ligation junction
+    FK_COPY = 4    // log10 copy (ext: j=0, lig: j=1)
+};
+// packed descriptor: kind[0:3] part[3:5] km1[5:7] slot_fwd[7:15] slot_rc[15:23] j[23:31]
+//   part: 0 ext, 1 insert, 2 lig.  km1 = k-1 (the divisor is len - km1).
+__host__ __device__ inline uint32_t fd_pack(uint32_t kind, uint32_t part, uint32_t km1, uint32_t sf, uint32_t sr, uint32_t j)
+{
+    return kind | (part << 3) | (km1 << 5) | (sf << 7) | (sr << 15) | (j << 23);
+}
+
+// per-warp shared-memory count slots (genomic orientation)
+//   insert: tri[64] di[16] mono[4] gc[1]  -> 85 slots
+//   arm:    di[16] mono[4] gc[1]          -> 21 slots
+#define SLOT_INS_TRI 0
+#define SLOT_INS_DI 64
+#define SLOT_INS_MONO 80
+#define SLOT_INS_GC 84
+#define SLOT_EXT_DI 85
+#define SLOT_EXT_MONO 101
+#define SLOT_EXT_GC 105
+#define SLOT_LIG_DI 106
+#define SLOT_LIG_MONO 122
+#define SLOT_LIG_GC 126
+#define SLOT_COUNT 128
+
+// ---------------------------------------------------------------------------
+// SVR contraction tile shape (k_svr.cu)
+// ---------------------------------------------------------------------------
+#define SVR_BM 64        // candidates per CTA tile
+#define SVR_BN 64        // support vectors per chunk
+#define SVR_BK 32        // k-slab staged per pipeline stage
+#define SVR_LDX 200      // padded row stride of the X tile in doubles (== 8 mod 16: conflict-free LDS.128)
+#define SVR_LDB 40       // padded row stride of an SV slab in doubles
+#define SVR_STAGES 4
+#define SVR_CONSUMER_WARPS 8
+#define SVR_THREADS ((SVR_CONSUMER_WARPS + 1) * 32)
+
+// ---------------------------------------------------------------------------
+// host context
+// ---------------------------------------------------------------------------
+struct HostConfig {
+    int max_capture = 0, min_capture = 0, inc = 1, max_mip_overlap = 0;
+    std::vector<int> ext_len, lig_len, oligo_sizes;
+    int n_cap = 0, max_sum = 0, min_sum = 0;
+};
+
+struct EventPair { cudaEvent_t a, b; int which; long units; };
+
+struct mg_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    std::string err;
+    // config
+    bool has_cfg = false;
+    HostConfig cfg;
+    DevConfig *d_cfg = nullptr;
+    // tables
+    uint32_t *d_fdesc = nullptr;    // [192] packed feature descriptors
+    double *d_logcopy = nullptr;    // [102] log10(copy) for copy 0..100 (glibc), [101] = 2.0
+    // model
+    bool has_model = false;
+    int n_sv = 0, n_sv_pad = 0;
+    double gamma = 0, rho = 0;
+    double *d_sv = nullptr;     // [n_sv_pad][192]
+    double *d_ss = nullptr;     // [n_sv_pad] ||s||^2 (incl. features beyond 192)
+    double *d_alpha = nullptr;  // [n_sv_pad], 0 in the padding
+    // workspace
+    double *d_x = nullptr;      // feature rows of the chunk in flight
+    size_t x_rows_cap = 0;
+    // timing
+    std::vector<EventPair> ev_pending;
+    std::vector<cudaEvent_t> ev_free;
+    mg_timings tm{};
+    cudaEvent_t sw_a = nullptr, sw_b = nullptr;
+    int sm_count = 148;
+};
+
+struct mg_panel {
+    mg_ctx *ctx = nullptr;
+    int n_regions = 0;
+    int64_t n_cand = 0;
+    int64_t n_valid_static = 0;
+    std::vector<int64_t> offsets;  // n+1
+    std::vector<DevRegion> h_regions;
+    DevRegion *d_regions = nullptr;
+    uint8_t *d_codes = nullptr;
+    int64_t n_codes = 0;
+    double *d_lrc = nullptr;       // [n_regions][44]
+    int *d_copies = nullptr;
+    uint8_t *d_valid = nullptr;
+    double *d_logistic = nullptr;
+    double *d_svr = nullptr;
+    double *d_feat = nullptr;      // only when features are fetched for the whole panel
+    bool has_logistic = false, has_svr = false, has_feat = false, has_valid = false;
+};
+
+#define CUDA_TRY(ctx, expr)                                                                  \
+    do {                                                                                     \
+        cudaError_t _e = (expr);                                                             \
+        if (_e != cudaSuccess) {                                                             \
+            (ctx)->err = std::string(#expr) + ": " + cudaGetErrorString(_e);                 \
+            return MG_ERR_CUDA;                                                              \
+        }                                                                                    \
+    } while (0)
+
+// kernels / launchers (defined in k_feat.cu, k_svr.cu)
+enum { TM_FEAT = 0, TM_SVR = 1, TM_OTHER = 2 };
+int mg_time_begin(mg_ctx *ctx, int which, long units);
+int mg_time_end(mg_ctx *ctx);
+
+int launch_encode(mg_ctx *ctx, const char *d_ascii, uint8_t *d_codes, int64_t n);
+int launch_lrc(mg_ctx *ctx, const uint8_t *d_codes, int n, int denom, double *d_out44);
+// grid front-end: candidates [g0, g1) of the panel; any of valid/logistic/x may be null.
+// x rows are written at row (g - g0).
+int launch_feat_grid(mg_ctx *ctx, const mg_panel *p, int64_t g0, int64_t g1, uint8_t *d_valid,
+                     double *d_logistic, double *d_x);
+// explicit front-end
+int launch_feat_explicit(mg_ctx *ctx, const DevCand *d_cands, const uint8_t *d_codes, const double *d_lrc,
+                         int64_t n, double *d_logistic, double *d_x);
+// SVR: rows [0, n) of d_x (ld 192, padded to a multiple of SVR_BM rows) -> d_out[n]
+// d_valid (nullable): rows with valid[g]==0 are written as NaN.
+int launch_svr(mg_ctx *ctx, const double *d_x, int64_t n, const uint8_t *d_valid, double *d_out);
+int launch_svr_setup(mg_ctx *ctx);
+int mg_upload_lrc_tables(mg_ctx *ctx, const uint8_t *k, const uint8_t *code);
+int launch_svr_direct(mg_ctx *ctx, const double *d_x, int64_t n, int64_t ld, double *d_out);

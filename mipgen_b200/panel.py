@@ -172,11 +172,14 @@ def write_svr_model(path: str, sv: np.ndarray, alpha: np.ndarray, gamma: float, 
     os.replace(tmp, path)
 
 
-def calibrate(alpha: np.ndarray, raw_scores: np.ndarray, median: float = 1.8, sigma: float = 0.45):
-    """Scale alpha and pick rho so that scores a*f - rho have the given median / spread
-    (thresholds 1.5 / 2.2 must be exercised)."""
+def calibrate(alpha: np.ndarray, raw_scores: np.ndarray, median: float = 1.8, upper: float = 2.2,
+              frac_above: float = 0.15):
+    """Scale alpha and pick rho so that scores a*f - rho have the given median and a
+    `frac_above` share above `upper` (the 1.5 / 2.2 thresholds and the
+    optimal-score shortcuts of mipgen.cpp:430,434 must be exercised)."""
     f = raw_scores[np.isfinite(raw_scores)]
-    sd = float(np.std(f)) or 1.0
-    a = sigma / sd
-    rho = a * float(np.median(f)) - median
+    q50, qhi = np.quantile(f, [0.5, 1.0 - frac_above])
+    spread = float(qhi - q50) or 1.0
+    a = (upper - median) / spread
+    rho = a * float(q50) - median
     return alpha * a, rho
