@@ -174,13 +174,15 @@ k_svr_dmma(const double *__restrict__ x, int64_t n, const double *__restrict__ s
                     for (int mi = 0; mi < 2; mi++) a[mi] = *reinterpret_cast<const double2 *>(As + mi * 8 * SVR_LDX + kb * 8);
 #pragma unroll
                     for (int ni = 0; ni < 4; ni++) b[ni] = *reinterpret_cast<const double2 *>(Bp + ni * 8 * SVR_LDB + kb * 8);
+                    // two passes over the 8 accumulators so dependent DMMAs sit 8 instructions apart
 #pragma unroll
                     for (int mi = 0; mi < 2; mi++)
 #pragma unroll
-                        for (int ni = 0; ni < 4; ni++) {
-                            dmma884(acc[mi][ni][0], acc[mi][ni][1], a[mi].x, b[ni].x);  // k = k0 + {0,2,4,6}
-                            dmma884(acc[mi][ni][0], acc[mi][ni][1], a[mi].y, b[ni].y);  // k = k0 + {1,3,5,7}
-                        }
+                        for (int ni = 0; ni < 4; ni++) dmma884(acc[mi][ni][0], acc[mi][ni][1], a[mi].x, b[ni].x);  // k = k0 + {0,2,4,6}
+#pragma unroll
+                    for (int mi = 0; mi < 2; mi++)
+#pragma unroll
+                        for (int ni = 0; ni < 4; ni++) dmma884(acc[mi][ni][0], acc[mi][ni][1], a[mi].y, b[ni].y);  // k = k0 + {1,3,5,7}
                 }
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&empty[stage]);
@@ -229,8 +231,9 @@ k_svr_dmma(const double *__restrict__ x, int64_t n, const double *__restrict__ s
 //   sum_k (x_k - s_k)^2 left to right with separately rounded mul/add (svm.cpp:330-365),
 //   exp, then sum_i alpha_i k_i left to right, then - rho (svm.cpp:2511-2516).
 __global__ void __launch_bounds__(64) k_svr_direct(const double *__restrict__ x, int64_t n, int64_t ld,
-                                                   const double *__restrict__ sv, const double *__restrict__ alpha, int n_sv,
-                                                   double gamma, double rho, double *__restrict__ out)
+                                                   const double *__restrict__ sv, const double *__restrict__ alpha,
+                                                   const double *__restrict__ tail, int n_sv, double gamma, double rho,
+                                                   double *__restrict__ out)
 {
     __shared__ double srow[MG_NFEAT];
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -245,6 +248,7 @@ __global__ void __launch_bounds__(64) k_svr_direct(const double *__restrict__ x,
             double d = __dsub_rn(xr[k], srow[k]);
             sum = __dadd_rn(sum, __dmul_rn(d, d));
         }
+        if (tail[j] != 0.0) sum = __dadd_rn(sum, tail[j]);  // SV features beyond index 192: + y*y (svm.cpp:360-364)
         double kv = exp(__dmul_rn(-gamma, sum));
         total = __dadd_rn(total, __dmul_rn(alpha[j], kv));
     }
@@ -275,8 +279,8 @@ int launch_svr_direct(mg_ctx *ctx, const double *d_x, int64_t n, int64_t ld, dou
 {
     if (n <= 0) return MG_OK;
     mg_time_begin(ctx, TM_OTHER, n);
-    k_svr_direct<<<(unsigned)((n + 63) / 64), 64, 0, ctx->stream>>>(d_x, n, ld, ctx->d_sv, ctx->d_alpha, ctx->n_sv, ctx->gamma,
-                                                                   ctx->rho, d_out);
+    k_svr_direct<<<(unsigned)((n + 63) / 64), 64, 0, ctx->stream>>>(d_x, n, ld, ctx->d_sv, ctx->d_alpha, ctx->d_tail, ctx->n_sv,
+                                                                   ctx->gamma, ctx->rho, d_out);
     mg_time_end(ctx);
     CUDA_TRY(ctx, cudaGetLastError());
     return MG_OK;

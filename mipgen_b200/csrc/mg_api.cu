@@ -181,8 +181,8 @@ extern "C" int mg_create(int device, mg_ctx **out)
 
 static void free_model(mg_ctx *ctx)
 {
-    cudaFree(ctx->d_sv); cudaFree(ctx->d_ss); cudaFree(ctx->d_alpha);
-    ctx->d_sv = ctx->d_ss = ctx->d_alpha = nullptr;
+    cudaFree(ctx->d_sv); cudaFree(ctx->d_ss); cudaFree(ctx->d_alpha); cudaFree(ctx->d_tail);
+    ctx->d_sv = ctx->d_ss = ctx->d_alpha = ctx->d_tail = nullptr;
     ctx->has_model = false;
 }
 
@@ -308,7 +308,7 @@ static int upload_model(mg_ctx *ctx, const std::vector<double> &dense, const std
     cudaStreamSynchronize(ctx->stream);
     free_model(ctx);
     int pad = std::max(SVR_BN, (n_sv + SVR_BN - 1) / SVR_BN * SVR_BN);
-    std::vector<double> sv((size_t)pad * MG_NFEAT, 0.0), ss(pad, 0.0), al(pad, 0.0);
+    std::vector<double> sv((size_t)pad * MG_NFEAT, 0.0), ss(pad, 0.0), al(pad, 0.0), tl(pad, 0.0);
     for (int i = 0; i < n_sv; i++) {
         double s = 0.0;
         for (int k = 0; k < MG_NFEAT; k++) {
@@ -317,11 +317,14 @@ static int upload_model(mg_ctx *ctx, const std::vector<double> &dense, const std
             s += v * v;
         }
         ss[i] = s + tail[i];
+        tl[i] = tail[i];
         al[i] = alpha[i];
     }
     CUDA_TRY(ctx, cudaMalloc(&ctx->d_sv, sv.size() * 8));
     CUDA_TRY(ctx, cudaMalloc(&ctx->d_ss, ss.size() * 8));
     CUDA_TRY(ctx, cudaMalloc(&ctx->d_alpha, al.size() * 8));
+    CUDA_TRY(ctx, cudaMalloc(&ctx->d_tail, tl.size() * 8));
+    CUDA_TRY(ctx, cudaMemcpy(ctx->d_tail, tl.data(), tl.size() * 8, cudaMemcpyHostToDevice));
     CUDA_TRY(ctx, cudaMemcpy(ctx->d_sv, sv.data(), sv.size() * 8, cudaMemcpyHostToDevice));
     CUDA_TRY(ctx, cudaMemcpy(ctx->d_ss, ss.data(), ss.size() * 8, cudaMemcpyHostToDevice));
     CUDA_TRY(ctx, cudaMemcpy(ctx->d_alpha, al.data(), al.size() * 8, cudaMemcpyHostToDevice));

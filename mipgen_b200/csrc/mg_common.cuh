@@ -123,6 +123,7 @@ struct mg_ctx {
     double *d_sv = nullptr;     // [n_sv_pad][192]
     double *d_ss = nullptr;     // [n_sv_pad] ||s||^2 (incl. features beyond 192)
     double *d_alpha = nullptr;  // [n_sv_pad], 0 in the padding
+    double *d_tail = nullptr;   // [n_sv_pad] sum of squares of SV features with index > 192
     // workspace
     double *d_x = nullptr;      // feature rows of the chunk in flight
     size_t x_rows_cap = 0;
