@@ -14,8 +14,11 @@
 // CTA = 8 consumer warps + 1 producer warp, one 64-candidate tile per CTA:
 //   * the tile's 64 x 192 feature rows are bulk-copied (cp.async.bulk -> UBLKCP, the
 //     TMA engine's non-tensor path) once into padded shared memory and stay resident;
-//   * support vectors stream through a 4-stage ring of 64 SV x 32 k slabs, each slab
-//     64 row-wise bulk copies completing on an mbarrier (full/empty pairs);
+//   * support vectors stream through a 4-stage ring of 64 SV x 32 k slabs.  The model is
+//     re-tiled once at upload into exactly the padded slab layout shared memory wants, so a
+//     slab is ONE 20 KB bulk copy completing on an mbarrier (full/empty pairs) -- the first
+//     version issued 64 row copies of 256 B per slab and the consumers waited on the TMA
+//     engine for a third of their cycles (profiles/r01_k_svr_v1_ncu.md);
 //   * consumer warp (wm, wn) owns a 16 x 32 block of the 64 x 64 chunk: per 8-wide
 //     k-block 2 + 4 conflict-free LDS.128 feed 16 DMMAs (k is interleaved even/odd so
 //     one 16-byte load serves two k4 steps);
@@ -74,7 +77,7 @@ constexpr int kBsDoubles = SVR_BN * SVR_LDB;              // 2560 per stage
 constexpr size_t kSmemBytes = (size_t)(kXsDoubles + SVR_STAGES * kBsDoubles + 2 * SVR_BM) * 8 + 16 * 8 + SVR_BM * 4;
 
 __global__ void __launch_bounds__(SVR_THREADS, 1)
-k_svr_dmma(const double *__restrict__ x, int64_t n, const double *__restrict__ sv, const double *__restrict__ ss,
+k_svr_dmma(const double *__restrict__ x, int64_t n, const double *__restrict__ sv_tiled, const double *__restrict__ ss,
            const double *__restrict__ alpha, int n_sv_pad, double gamma, double rho, const uint8_t *__restrict__ valid,
            double *__restrict__ out)
 {
@@ -112,14 +115,11 @@ k_svr_dmma(const double *__restrict__ x, int64_t n, const double *__restrict__ s
                 const int stage = q % SVR_STAGES;
                 const uint32_t phase = (q / SVR_STAGES) & 1;
                 if (q >= SVR_STAGES) mbar_wait(&empty[stage], phase ^ 1);
-                if (lane == 0) mbar_arrive_expect_tx(&full[stage], SVR_BN * SVR_BK * 8);
-                __syncwarp();
-#pragma unroll
-                for (int h = 0; h < SVR_BN / 32; h++) {
-                    int r = lane + 32 * h;
-                    bulk_g2s(Bs + stage * kBsDoubles + r * SVR_LDB,
-                             sv + ((int64_t)chunk * SVR_BN + r) * MG_NFEAT + slab * SVR_BK, SVR_BK * 8, &full[stage]);
+                if (lane == 0) {
+                    mbar_arrive_expect_tx(&full[stage], kBsDoubles * 8);
+                    bulk_g2s(Bs + stage * kBsDoubles, sv_tiled + ((int64_t)chunk * kSlabs + slab) * kBsDoubles, kBsDoubles * 8, &full[stage]);
                 }
+                __syncwarp();
             }
         }
     } else {
@@ -268,7 +268,7 @@ int launch_svr(mg_ctx *ctx, const double *d_x, int64_t n, const uint8_t *d_valid
     if (n <= 0) return MG_OK;
     const int64_t tiles = (n + SVR_BM - 1) / SVR_BM;
     mg_time_begin(ctx, TM_SVR, n);
-    k_svr_dmma<<<(unsigned)tiles, SVR_THREADS, kSmemBytes, ctx->stream>>>(d_x, n, ctx->d_sv, ctx->d_ss, ctx->d_alpha, ctx->n_sv_pad,
+    k_svr_dmma<<<(unsigned)tiles, SVR_THREADS, kSmemBytes, ctx->stream>>>(d_x, n, ctx->d_sv_tiled, ctx->d_ss, ctx->d_alpha, ctx->n_sv_pad,
                                                                        ctx->gamma, ctx->rho, d_valid, d_out);
     mg_time_end(ctx);
     CUDA_TRY(ctx, cudaGetLastError());

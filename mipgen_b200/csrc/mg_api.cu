@@ -181,8 +181,8 @@ extern "C" int mg_create(int device, mg_ctx **out)
 
 static void free_model(mg_ctx *ctx)
 {
-    cudaFree(ctx->d_sv); cudaFree(ctx->d_ss); cudaFree(ctx->d_alpha); cudaFree(ctx->d_tail);
-    ctx->d_sv = ctx->d_ss = ctx->d_alpha = ctx->d_tail = nullptr;
+    cudaFree(ctx->d_sv); cudaFree(ctx->d_sv_tiled); cudaFree(ctx->d_ss); cudaFree(ctx->d_alpha); cudaFree(ctx->d_tail);
+    ctx->d_sv = ctx->d_sv_tiled = ctx->d_ss = ctx->d_alpha = ctx->d_tail = nullptr;
     ctx->has_model = false;
 }
 
@@ -320,6 +320,14 @@ static int upload_model(mg_ctx *ctx, const std::vector<double> &dense, const std
         tl[i] = tail[i];
         al[i] = alpha[i];
     }
+    // slab image: [chunk][slab][row][SVR_LDB], the last SVR_LDB-SVR_BK doubles of a row are padding
+    const int n_slabs = MG_NFEAT / SVR_BK;
+    std::vector<double> tiled((size_t)(pad / SVR_BN) * n_slabs * SVR_BN * SVR_LDB, 0.0);
+    for (int i = 0; i < pad; i++)
+        for (int k = 0; k < MG_NFEAT; k++)
+            tiled[(((size_t)(i / SVR_BN) * n_slabs + k / SVR_BK) * SVR_BN + i % SVR_BN) * SVR_LDB + k % SVR_BK] = sv[(size_t)i * MG_NFEAT + k];
+    CUDA_TRY(ctx, cudaMalloc(&ctx->d_sv_tiled, tiled.size() * 8));
+    CUDA_TRY(ctx, cudaMemcpy(ctx->d_sv_tiled, tiled.data(), tiled.size() * 8, cudaMemcpyHostToDevice));
     CUDA_TRY(ctx, cudaMalloc(&ctx->d_sv, sv.size() * 8));
     CUDA_TRY(ctx, cudaMalloc(&ctx->d_ss, ss.size() * 8));
     CUDA_TRY(ctx, cudaMalloc(&ctx->d_alpha, al.size() * 8));

@@ -120,7 +120,8 @@ struct mg_ctx {
     bool has_model = false;
     int n_sv = 0, n_sv_pad = 0;
     double gamma = 0, rho = 0;
-    double *d_sv = nullptr;     // [n_sv_pad][192]
+    double *d_sv = nullptr;     // [n_sv_pad][192] row-major (cross-check kernel)
+    double *d_sv_tiled = nullptr; // [n_sv_pad/64][6][64][SVR_LDB]: the padded smem slab image K-svr bulk-copies
     double *d_ss = nullptr;     // [n_sv_pad] ||s||^2 (incl. features beyond 192)
     double *d_alpha = nullptr;  // [n_sv_pad], 0 in the padding
     double *d_tail = nullptr;   // [n_sv_pad] sum of squares of SV features with index > 192
