@@ -77,6 +77,8 @@ typedef struct {
     const int *copies; /* [n_oligo_sizes][seq_len]: copy number of the oligo of size
                           oligo_sizes[k] starting at seq index i (copy_chr_start_stop,
                           mipgen.cpp:83, 612-613; 0 = absent key); NULL => every copy is 1   */
+    int scan_begin;    /* optional explicit range of scan starts [scan_begin, scan_end];      */
+    int scan_end;      /*   both 0 => the reference's rule (mipgen.cpp:421-425)               */
 } mg_region;
 
 /* One SVMipv4 object as mipgen.cpp leaves it after design_mip: strand-oriented strings

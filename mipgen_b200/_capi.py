@@ -33,7 +33,7 @@ class MgConfig(C.Structure):
 class MgRegion(C.Structure):
     _fields_ = [("seq", C.c_char_p), ("seq_len", C.c_int), ("seq_start", C.c_int), ("seq_stop", C.c_int),
                 ("start_flanked", C.c_int), ("stop_flanked", C.c_int), ("lrc", c_double_p),
-                ("copies", c_int_p)]
+                ("copies", c_int_p), ("scan_begin", C.c_int), ("scan_end", C.c_int)]
 
 
 class MgCandidate(C.Structure):
@@ -130,7 +130,7 @@ def _c_regions(regions: Sequence[Region]):
         cop = np.ascontiguousarray(r.copies, np.int32) if r.copies is not None else None
         keep += [lrc, cop, r.seq]
         arr[i] = MgRegion(r.seq, len(r.seq), r.seq_start, r.seq_stop, r.start_flanked, r.stop_flanked,
-                          _ptr(lrc, c_double_p), _ptr(cop, c_int_p))
+                          _ptr(lrc, c_double_p), _ptr(cop, c_int_p), getattr(r, "scan_begin", 0), getattr(r, "scan_end", 0))
     return arr, keep
 
 

@@ -558,6 +558,7 @@ extern "C" int mg_score_candidates(mg_ctx *ctx, const mg_candidate *cands, long 
 // ---------------------------------------------------------------------------
 static int first_scan_start(const HostConfig &c, const mg_region *r)
 {
+    if (r->scan_begin > 0) return r->scan_begin;
     // mipgen.cpp:421-425 (the loop pre-increments)
     int cur = r->start_flanked - c.max_capture + c.max_sum;
     if (cur < 0) cur = 0;
@@ -566,7 +567,8 @@ static int first_scan_start(const HostConfig &c, const mg_region *r)
 
 static int n_scan(const HostConfig &c, const mg_region *r)
 {
-    int n = r->stop_flanked - first_scan_start(c, r) + 1;
+    int last = (r->scan_begin > 0 && r->scan_end > 0) ? r->scan_end : r->stop_flanked;
+    int n = last - first_scan_start(c, r) + 1;
     return n < 0 ? 0 : n;
 }
 

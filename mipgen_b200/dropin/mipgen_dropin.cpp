@@ -192,8 +192,7 @@ static void run_batch(const Featurev5 *f, int s0, int s1, bool want_svr, const d
         if (std::find(pairs.begin(), pairs.end(), p) == pairs.end()) pairs.push_back(p);
     }
     std::stable_sort(pairs.begin(), pairs.end(), [](const std::pair<int, int> &a, const std::pair<int, int> &c) { return a.first + a.second > c.first + c.second; });
-    int max_sum = 0;
-    for (auto &p : pairs) { b.ext.push_back(p.first); b.lig.push_back(p.second); max_sum = std::max(max_sum, p.first + p.second); }
+    for (auto &p : pairs) { b.ext.push_back(p.first); b.lig.push_back(p.second); }
 
     mg_config cfg;
     memset(&cfg, 0, sizeof cfg);
@@ -215,14 +214,11 @@ static void run_batch(const Featurev5 *f, int s0, int s1, bool want_svr, const d
     r.seq_len = (int)b.seq.size();
     r.seq_start = b.seq_start;
     r.seq_stop = f->chromosomal_sequence_stop_position;
-    // a pseudo region whose scan range (mipgen.cpp:421-425) is exactly [s0, s1]
-    r.start_flanked = s0 - 1 + b.max_cap - max_sum;
-    r.stop_flanked = s1;
+    r.start_flanked = f->start_position_flanked;
+    r.stop_flanked = f->stop_position_flanked;
+    r.scan_begin = s0;  // explicit scan range: the rest of the region from the caller's position
+    r.scan_end = s1;
     r.lrc = b.lrc;
-    if (mg_first_scan_start(ctx(), &r) != s0) {  // clamped at the chromosome start: fall back to one row at a time
-        fprintf(stderr, "[mipgen_b200] fatal: internal scan-range mismatch (%d vs %d)\n", mg_first_scan_start(ctx(), &r), s0);
-        exit(70);
-    }
     int64_t n = mg_grid_size(ctx(), &r);
     b.valid.resize((size_t)n);
     b.logistic.resize((size_t)n);
