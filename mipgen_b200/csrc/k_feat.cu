@@ -6,20 +6,31 @@
 //   SVMipv4::get_parameters            SVMipv4.cpp:60-113   (192 FP64 features)
 //   SVMipv4::get_score                 SVMipv4.cpp:114-248  (logistic score)
 //
-// Mapping: one warp owns 32 consecutive candidates.  For each of them the 32 lanes
-// count k-mers cooperatively (one shared-memory atomic per base: every base votes for
-// its "extended trimer" (X, Y|none, Z|none); di- and mono-nucleotide counts are sums of
-// those bins), derive the count slots, and write the candidate's 192-double feature row
-// with six coalesced 256-byte stores.  The minus strand is never materialised: counts
-// are taken on the genomic window and looked up through the reverse-complement k-mer
-// slot.  Lane c keeps the handful of integers the logistic model needs for candidate c;
-// after 32 candidates every lane evaluates one 70-term polynomial, so the epilogue runs
-// at full lane occupancy and the scores leave as one coalesced 256-byte store.
+// Two front-ends share the feature layout and the logistic epilogue:
 //
-// All feature values are a single IEEE division of two small integers, and the logistic
-// exponent is summed in the reference's order with explicit round-to-nearest mul/add
-// (no FMA contraction), so both are bit-identical to the CPU code; only pow() differs
-// (CUDA vs glibc, <= 2 ulp).
+// (1) k_feat_window -- the region grid (the hot one).  A CTA takes a WINDOW of consecutive
+//     scan starts of one region.  It stages the window's span of the region (<= ~400 bases)
+//     in shared memory and builds 88 prefix-count tables over it (64 tri-, 16 di-, 4
+//     mono-nucleotides, G+C, N-or-'-', non-ACGT, GC/AT class transitions; uint16).  Every
+//     k-mer count of every arm / insert of every candidate of the window is then a difference
+//     of two table entries: no per-candidate scanning at all.  A warp writes one candidate's
+//     192-double row with six coalesced 256-byte stores (each lane: 6 x {2 LDS.U16, subtract,
+//     divide}); afterwards each lane evaluates the logistic model for its own candidate.
+//     The minus strand is never materialised: counts are taken on the genomic window and
+//     looked up through the reverse-complement k-mer's table.
+//     Division: count/(len-k+1) with small integer operands is computed as
+//     q0 = c*rn, r = fma(-q0, n, c), q = fma(r, rn, q0) with rn = RN(1/n) from a shared-memory
+//     table -- bit-identical to IEEE division for every 0 <= c, 1 <= n <= 4096
+//     (exhaustively checked on the CPU: tests/test_division_identity.py).
+//
+// (2) k_feat_explicit -- explicit, already strand-oriented strings (the SVMipv4 object
+//     interface; cfg1 and the drop-in's exception path).  One warp per candidate counts
+//     k-mers with one shared-memory atomic per base.
+//
+// All feature values are a single correctly rounded division of two small integers, and the
+// logistic exponent is summed in the reference's order with explicit round-to-nearest
+// mul/add (no FMA contraction), so both are bit-identical to the CPU code; only pow()
+// differs (CUDA vs glibc, <= 2 ulp).
 #include "mg_common.cuh"
 #include "logistic_terms.inc"
 
@@ -253,6 +264,75 @@ __device__ __forceinline__ double logistic_score(const Stash &s, const double *_
 }
 
 // ------------------------------- grid front-end -------------------------------
+// prefix-table rows
+constexpr int PF_TRI = 0, PF_DI = 64, PF_MONO = 80, PF_GC = 84, PF_NDASH = 85, PF_OTHER = 86, PF_TRANS = 87, PF_ROWS = 88;
+constexpr int kRecipN = 512;
+
+struct WinSmem {
+    const uint16_t *P;   // [PF_ROWS][stride]
+    int stride;
+    const uint8_t *codes;  // span codes (+3 sentinels)
+    const double *rn;    // [kRecipN] RN(1/n)
+    const double *lrc;   // [44]
+    int span_len;
+};
+
+// occurrences of the k-mer of table `row` that lie inside [a, a+n)  (span-relative)
+__device__ __forceinline__ int pf_count(const WinSmem &w, int row, int a, int n, int k)
+{
+    const int end = a + n - k + 1;
+    if (end <= a) return 0;
+    const uint16_t *r = w.P + row * w.stride;
+    return (int)(uint16_t)(r[end] - r[a]);
+}
+
+__device__ __forceinline__ double small_div(const WinSmem &w, int c, int n)
+{
+    if (n > 0 && n < kRecipN) {
+        const double a = (double)c, b = (double)n, y = w.rn[n];
+        const double q0 = __dmul_rn(a, y);
+        const double r = __fma_rn(-q0, b, a);
+        return __fma_rn(r, y, q0);
+    }
+    return __ddiv_rn((double)c, (double)n);
+}
+
+struct Geo {
+    int ok;                        // passes the static skips and lies inside the sequence
+    int rc;                        // strand
+    int ext_a, lig_a, tgt_a;       // span-relative window starts
+    int ext_n, lig_n, tgt_n;       // characters present
+    int ext_len, lig_len, scan_size;
+    int ext_start, lig_start;      // chromosome coordinates (copy look-up)
+};
+
+__device__ __forceinline__ Geo decode_candidate(const DevConfig *__restrict__ cfg, const DevRegion &r, int span0, int si, int rem)
+{
+    Geo g;
+    const int n_pairs = cfg->n_pairs, inc = cfg->inc;
+    g.rc = rem & 1;
+    rem >>= 1;
+    const int ci = rem / n_pairs, p = rem - ci * n_pairs;
+    const int s = r.first_scan + si, cap = cfg->max_capture - ci * inc;
+    const int e = cfg->ext_len[p], l = cfg->lig_len[p];
+    // static skips: mipgen.cpp:429, 443, 444
+    bool ok = !(cap > r.stop_flanked - r.start_flanked + cfg->max_mip_overlap && cap - inc >= cfg->min_capture);
+    ok = ok && !(s - e <= 0 || s - l <= 0);
+    ok = ok && !(s + cap - e - 1 > r.seq_stop || s + cap - l - 1 > r.seq_stop);
+    const int t = s + cap - (e + l) - 1;  // scan_stop (:449)
+    g.ext_len = e; g.lig_len = l; g.scan_size = t - s + 1;
+    g.ext_start = g.rc ? t + 1 : s - e;   // Plus/MinusSVMipv4 ctors
+    g.lig_start = g.rc ? s - l : t + 1;
+    const int eo = g.ext_start - r.seq_start, lo = g.lig_start - r.seq_start, to = s - r.seq_start;
+    // std::string::substr(off,len) throws for off > size; it clamps the length otherwise
+    ok = ok && eo >= 0 && lo >= 0 && to >= 0 && eo <= r.seq_len && lo <= r.seq_len && to <= r.seq_len && g.scan_size >= 0;
+    g.ext_n = min(e, r.seq_len - eo); g.lig_n = min(l, r.seq_len - lo); g.tgt_n = min(g.scan_size, r.seq_len - to);
+    g.ext_a = eo - span0; g.lig_a = lo - span0; g.tgt_a = to - span0;
+    ok = ok && g.ext_a >= 0 && g.lig_a >= 0 && g.tgt_a >= 0;  // always true for statically valid candidates
+    g.ok = ok;
+    return g;
+}
+
 __device__ __forceinline__ int copy_lookup(const DevConfig *__restrict__ cfg, const DevRegion &r,
                                            const int *__restrict__ copies, int start, int len)
 {
@@ -266,80 +346,165 @@ __device__ __forceinline__ int copy_lookup(const DevConfig *__restrict__ cfg, co
     return 0;  // absent key: map::operator[] yields 0 (mipgen.cpp:612-613)
 }
 
-__global__ void __launch_bounds__(kWarpsPerBlock * 32)
-k_feat_grid(const DevConfig *__restrict__ cfg, const DevRegion *__restrict__ regions, int n_regions,
-            const uint8_t *__restrict__ codes, const double *__restrict__ lrc_all, const int *__restrict__ copies,
-            const uint32_t *__restrict__ fdesc, const double *__restrict__ logtab, int64_t g0, int64_t g1,
-            uint8_t *__restrict__ valid, double *__restrict__ logistic, double *__restrict__ x)
+__device__ __forceinline__ int junction_code(const WinSmem &w, const Geo &g)
 {
-    __shared__ int smem[kWarpsPerBlock * kWarpSmemInts];
+    if (g.lig_n < 2) return -1;
+    const uint32_t j0 = g.rc ? w.codes[g.lig_a + g.lig_n - 1] : w.codes[g.lig_a];
+    const uint32_t j1 = g.rc ? w.codes[g.lig_a + g.lig_n - 2] : w.codes[g.lig_a + 1];
+    if (j0 >= 4 || j1 >= 4) return -1;
+    return g.rc ? (int)((3 - j0) * 4 + (3 - j1)) : (int)(j0 * 4 + j1);
+}
+
+__global__ void __launch_bounds__(kWarpsPerBlock * 32, 3)
+k_feat_window(const DevConfig *__restrict__ cfg, const DevRegion *__restrict__ regions, const DevTask *__restrict__ tasks,
+              int task0, int task1, const uint8_t *__restrict__ codes, const double *__restrict__ lrc_all,
+              const int *__restrict__ copies, const uint32_t *__restrict__ fdesc, const double *__restrict__ logtab,
+              int64_t g_base, uint8_t *__restrict__ valid, double *__restrict__ logistic, double *__restrict__ x, int stride)
+{
+    extern __shared__ __align__(16) uint8_t smem_raw[];
+    double *rn = reinterpret_cast<double *>(smem_raw);            // [kRecipN]
+    double *lrc_s = rn + kRecipN;                                  // [44]
+    uint16_t *P = reinterpret_cast<uint16_t *>(lrc_s + MG_NLRC);   // [PF_ROWS][stride]
+    uint8_t *codes_s = reinterpret_cast<uint8_t *>(P + PF_ROWS * stride);
+
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    int *sm = smem + warp * kWarpSmemInts;
     uint32_t fd[6];
 #pragma unroll
     for (int m = 0; m < 6; m++) fd[m] = fdesc[lane + 32 * m];
+    for (int i = threadIdx.x; i < kRecipN; i += blockDim.x) rn[i] = i ? __ddiv_rn(1.0, (double)i) : 0.0;
 
-    const int n_pairs = cfg->n_pairs, n_cap = cfg->n_cap, inc = cfg->inc;
-    const int64_t per_scan = (int64_t)n_cap * n_pairs * 2;
-    const int64_t n_blocks = (g1 - g0 + 31) >> 5;
-    int ri = 0;
-    DevRegion r = regions[0];
-    int64_t r_end = (n_regions > 1) ? regions[1].grid_off : INT64_MAX;
+    const int per_scan = cfg->n_cap * cfg->n_pairs * 2;
+    const int max_arm = cfg->max_arm, min_arm = cfg->min_arm;
 
-    for (int64_t blk = (int64_t)blockIdx.x * kWarpsPerBlock + warp; blk < n_blocks; blk += (int64_t)gridDim.x * kWarpsPerBlock) {
-        Stash st;
-        st.state = 0;
-        const int64_t gb = g0 + (blk << 5);
-        for (int c = 0; c < 32; c++) {
-            const int64_t g = gb + c;
-            if (g >= g1) break;
-            if (g < r.grid_off || g >= r_end) {  // find the region of g (uniform binary search)
-                int lo = 0, hi = n_regions - 1;
-                while (lo < hi) {
-                    int mid = (lo + hi + 1) >> 1;
-                    if (regions[mid].grid_off <= g) lo = mid; else hi = mid - 1;
-                }
-                ri = lo;
-                r = regions[ri];
-                r_end = (ri + 1 < n_regions) ? regions[ri + 1].grid_off : INT64_MAX;
+    for (int ti = task0 + blockIdx.x; ti < task1; ti += gridDim.x) {
+        const DevTask tk = tasks[ti];
+        const DevRegion r = regions[tk.region];
+        // span of the region this window can touch: [first scan start - longest arm, last scan start + max capture - shortest arm)
+        const int s_first = r.first_scan + tk.si0, s_last = s_first + tk.nsi - 1;
+        int span0 = s_first - max_arm - r.seq_start;
+        if (span0 < 0) span0 = 0;
+        int span1 = s_last + cfg->max_capture - min_arm - r.seq_start;
+        if (span1 > r.seq_len) span1 = r.seq_len;
+        const int span_len = span1 > span0 ? span1 - span0 : 0;
+        __syncthreads();  // previous task's tables are no longer read
+        for (int i = threadIdx.x; i < span_len + 3; i += blockDim.x) codes_s[i] = i < span_len ? codes[r.seq_off + span0 + i] : (uint8_t)B_NONE;
+        if (threadIdx.x < MG_NLRC) lrc_s[threadIdx.x] = lrc_all ? lrc_all[(int64_t)tk.region * MG_NLRC + threadIdx.x] : 0.0;
+        __syncthreads();
+        if (threadIdx.x < PF_ROWS) {
+            const int row = threadIdx.x;
+            uint16_t *pr = P + row * stride;
+            uint32_t cnt = 0;
+            pr[0] = 0;
+            uint32_t cm = B_NONE, c0 = codes_s[0], c1 = codes_s[1], c2 = codes_s[2];
+            for (int p = 0; p < span_len; p++) {
+                bool hit;
+                if (row < PF_DI) hit = c0 < 4 && c1 < 4 && c2 < 4 && (int)(c0 * 16 + c1 * 4 + c2) == row;
+                else if (row < PF_MONO) hit = c0 < 4 && c1 < 4 && (int)(c0 * 4 + c1) == row - PF_DI;
+                else if (row < PF_GC) hit = (int)c0 == row - PF_MONO;
+                else if (row == PF_GC) hit = c0 == B_C || c0 == B_G;
+                else if (row == PF_NDASH) hit = c0 == B_N || c0 == B_DASH;
+                else if (row == PF_OTHER) hit = c0 >= 4;
+                else hit = p > 0 && base_class(c0) != base_class(cm);
+                cnt += hit;
+                pr[p + 1] = (uint16_t)cnt;
+                cm = c0; c0 = c1; c1 = c2; c2 = codes_s[p + 3];
             }
-            const int64_t local = g - r.grid_off;
-            const int si = (int)(local / per_scan);
-            int rem = (int)(local - (int64_t)si * per_scan);
-            const int strand = rem & 1;
-            rem >>= 1;
-            const int ci = rem / n_pairs, p = rem - ci * n_pairs;
-            const int s = r.first_scan + si, cap = cfg->max_capture - ci * inc;
-            const int e = cfg->ext_len[p], l = cfg->lig_len[p];
-            // static skips: mipgen.cpp:429, 443, 444
-            bool ok = !(cap > r.stop_flanked - r.start_flanked + cfg->max_mip_overlap && cap - inc >= cfg->min_capture);
-            ok = ok && !(s - e <= 0 || s - l <= 0);
-            ok = ok && !(s + cap - e - 1 > r.seq_stop || s + cap - l - 1 > r.seq_stop);
-            const int t = s + cap - (e + l) - 1;  // scan_stop (:449)
-            View v;
-            v.rc = strand;
-            v.ext_len = e; v.lig_len = l; v.scan_size = t - s + 1;
-            const int ext_start = strand ? t + 1 : s - e;   // Plus/MinusSVMipv4 ctors
-            const int lig_start = strand ? s - l : t + 1;
-            const int eo = ext_start - r.seq_start, lo_ = lig_start - r.seq_start, to = s - r.seq_start;
-            // std::string::substr(off,len) throws for off > size; it clamps the length otherwise
-            ok = ok && eo >= 0 && lo_ >= 0 && to >= 0 && eo <= r.seq_len && lo_ <= r.seq_len && to <= r.seq_len && v.scan_size >= 0;
-            v.ok = ok;
-            const uint8_t *base = codes + r.seq_off;
-            v.ext = base + eo; v.lig = base + lo_; v.tgt = base + to;
-            v.ext_n = min(e, r.seq_len - eo); v.lig_n = min(l, r.seq_len - lo_); v.tgt_n = min(v.scan_size, r.seq_len - to);
-            v.ext_copy = 1; v.lig_copy = 1;
-            if (ok && r.copy_off >= 0) {
-                v.ext_copy = copy_lookup(cfg, r, copies, ext_start, e);
-                v.lig_copy = copy_lookup(cfg, r, copies, lig_start, l);
-            }
-            v.lrc = lrc_all ? lrc_all + (int64_t)ri * MG_NLRC : nullptr;
-            warp_candidate(v, sm, lane, fd, logtab, x ? x + (g - g0) * MG_NFEAT : nullptr, st, lane == c);
         }
-        const int64_t g = gb + lane;
-        if (g < g1) {
-            if (valid) valid[g] = st.state != 0;
-            if (logistic) logistic[g] = logistic_score(st, logtab);
+        __syncthreads();
+
+        WinSmem w;
+        w.P = P; w.stride = stride; w.codes = codes_s; w.rn = rn; w.lrc = lrc_s; w.span_len = span_len;
+        const int n_c = tk.nsi * per_scan;
+        for (int blk = warp; blk * 32 < n_c; blk += kWarpsPerBlock) {
+            // ---- feature rows: the warp writes candidate after candidate ----
+            if (x) {
+                const int jend = min(32, n_c - blk * 32);
+                for (int c = 0; c < jend; c++) {
+                    const int j = blk * 32 + c;
+                    const int si = j / per_scan;
+                    const Geo g = decode_candidate(cfg, r, span0, tk.si0 + si, j - si * per_scan);
+                    double *xrow = x + (tk.g0 + j - g_base) * MG_NFEAT;
+                    bool zero = !g.ok;
+                    int ext_copy = 1, lig_copy = 1, jcode = -1;
+                    if (g.ok) {
+                        // 'N' in an arm, or '-' in mip_seq (== '-' in an arm)   SVMipv4.cpp:63-68 -> 192 zeros
+                        zero = pf_count(w, PF_NDASH, g.ext_a, g.ext_n, 1) + pf_count(w, PF_NDASH, g.lig_a, g.lig_n, 1) > 0;
+                        jcode = junction_code(w, g);
+                        if (r.copy_off >= 0) {
+                            ext_copy = copy_lookup(cfg, r, copies, g.ext_start, g.ext_len);
+                            lig_copy = copy_lookup(cfg, r, copies, g.lig_start, g.lig_len);
+                        }
+                    }
+#pragma unroll
+                    for (int m = 0; m < 6; m++) {
+                        const uint32_t d = fd[m];
+                        const uint32_t kind = d & 7, part = (d >> 3) & 3, km1 = (d >> 5) & 3, jj = (d >> 23) & 255;
+                        const int len = part == 0 ? g.ext_len : (part == 1 ? g.scan_size : g.lig_len);
+                        double val;
+                        if (zero) val = 0.0;
+                        else if (kind == FK_RATIO) {
+                            const int a = part == 0 ? g.ext_a : (part == 1 ? g.tgt_a : g.lig_a);
+                            const int n = part == 0 ? g.ext_n : (part == 1 ? g.tgt_n : g.lig_n);
+                            const int row = g.rc ? (int)((d >> 15) & 255) : (int)((d >> 7) & 255);
+                            const int k = row == PF_GC ? 1 : (int)km1 + 1;
+                            val = small_div(w, pf_count(w, row, a, n, k), len - (int)km1);
+                        } else if (kind == FK_LEN) val = (double)len;
+                        else if (kind == FK_LRC) val = lrc_s[jj];
+                        else if (kind == FK_JUNC) val = (jcode == (int)jj) ? 1.0 : 0.0;
+                        else val = log_copy(jj == 0 ? ext_copy : lig_copy, logtab);
+                        xrow[lane + 32 * m] = val;
+                    }
+                }
+            }
+            // ---- validity + logistic score: one lane per candidate ----
+            const int j = blk * 32 + lane;
+            if (j < n_c && (valid || logistic)) {
+                const int si = j / per_scan;
+                const Geo g = decode_candidate(cfg, r, span0, tk.si0 + si, j - si * per_scan);
+                if (valid) valid[tk.g0 + j] = (uint8_t)g.ok;
+                if (logistic) {
+                    Stash st;
+                    st.state = 0;
+                    if (g.ok) {
+                        const bool invalid = pf_count(w, PF_NDASH, g.ext_a, g.ext_n, 1) + pf_count(w, PF_NDASH, g.lig_a, g.lig_n, 1) > 0;
+                        st.state = invalid ? 1 : 2;
+                        if (!invalid) {
+                            const int G = PF_MONO + (g.rc ? B_C : B_G), Cc = PF_MONO + (g.rc ? B_G : B_C), A = PF_MONO + (g.rc ? B_T : B_A);
+                            st.eg = pf_count(w, G, g.ext_a, g.ext_n, 1); st.ec = pf_count(w, Cc, g.ext_a, g.ext_n, 1); st.ea = pf_count(w, A, g.ext_a, g.ext_n, 1);
+                            st.lg = pf_count(w, G, g.lig_a, g.lig_n, 1); st.lc = pf_count(w, Cc, g.lig_a, g.lig_n, 1); st.la = pf_count(w, A, g.lig_a, g.lig_n, 1);
+                            st.tg = pf_count(w, G, g.tgt_a, g.tgt_n, 1); st.tc = pf_count(w, Cc, g.tgt_a, g.tgt_n, 1); st.ta = pf_count(w, A, g.tgt_a, g.tgt_n, 1);
+                            // run count (SVMipv4.cpp:118-141)
+                            const int nt = min(g.tgt_n, g.scan_size);
+                            int runs;
+                            if (pf_count(w, PF_OTHER, g.tgt_a, nt, 1) == 0) {
+                                const uint16_t *tr = P + PF_TRANS * stride;
+                                runs = 1 + (nt >= 2 ? (int)(uint16_t)(tr[g.tgt_a + nt] - tr[g.tgt_a + 1]) : 0);
+                            } else {
+                                // characters outside ACGT make the reference's state machine order dependent:
+                                // replay it literally, in stored-string order (rare path)
+                                int rr = 0;
+                                if (nt > 0) {
+                                    int last = base_class(g.rc ? codes_s[g.tgt_a + g.tgt_n - 1] : codes_s[g.tgt_a]);
+                                    for (int i = 1; i < nt; i++) {
+                                        const int cur = base_class(g.rc ? codes_s[g.tgt_a + g.tgt_n - 1 - i] : codes_s[g.tgt_a + i]);
+                                        if (cur == 0) { if (last != 0) { rr++; last = 0; } }
+                                        else { if (last != 1) { rr++; last = cur; } }
+                                    }
+                                }
+                                runs = rr + 1;
+                            }
+                            st.runs = runs; st.ext_len = g.ext_len; st.lig_len = g.lig_len; st.scan_size = g.scan_size;
+                            st.jcode = junction_code(w, g);
+                            st.ext_copy = 1; st.lig_copy = 1;
+                            if (r.copy_off >= 0) {
+                                st.ext_copy = copy_lookup(cfg, r, copies, g.ext_start, g.ext_len);
+                                st.lig_copy = copy_lookup(cfg, r, copies, g.lig_start, g.lig_len);
+                            }
+                        }
+                    }
+                    logistic[tk.g0 + j] = logistic_score(st, logtab);
+                }
+            }
         }
     }
 }
@@ -468,14 +633,30 @@ int launch_lrc(mg_ctx *ctx, const uint8_t *d_codes, int n, int denom, double *d_
     return MG_OK;
 }
 
-int launch_feat_grid(mg_ctx *ctx, const mg_panel *p, int64_t g0, int64_t g1, uint8_t *d_valid, double *d_logistic,
-                     double *d_x)
+size_t feat_window_smem(int stride, int span_cap)
 {
-    if (g1 <= g0) return MG_OK;
-    mg_time_begin(ctx, TM_FEAT, g1 - g0);
-    k_feat_grid<<<feat_grid_dim(ctx, g1 - g0), kWarpsPerBlock * 32, 0, ctx->stream>>>(
-        ctx->d_cfg, p->d_regions, p->n_regions, p->d_codes, p->d_lrc, p->d_copies, ctx->d_fdesc, ctx->d_logcopy, g0, g1,
-        d_valid, d_logistic, d_x);
+    return (size_t)kRecipN * 8 + MG_NLRC * 8 + (size_t)PF_ROWS * stride * 2 + (size_t)span_cap + 8;
+}
+
+int launch_feat_setup(mg_ctx *ctx)
+{
+    CUDA_TRY(ctx, cudaFuncSetAttribute(k_feat_window, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    return MG_OK;
+}
+
+int launch_feat_grid(mg_ctx *ctx, const mg_panel *p, int task0, int task1, int64_t g_base, int64_t n_cand, uint8_t *d_valid,
+                     double *d_logistic, double *d_x)
+{
+    if (task1 <= task0) return MG_OK;
+    const size_t smem = feat_window_smem(p->pf_stride, p->span_cap);
+    if (smem > 200 * 1024) { ctx->err = "capture size too large for the K-feat window tables"; return MG_ERR_INVALID; }
+    int blocks = task1 - task0;
+    const int cap = ctx->sm_count * 8;
+    if (blocks > cap) blocks = cap;
+    mg_time_begin(ctx, TM_FEAT, n_cand);
+    k_feat_window<<<blocks, kWarpsPerBlock * 32, smem, ctx->stream>>>(ctx->d_cfg, p->d_regions, p->d_tasks, task0, task1, p->d_codes,
+                                                                      p->d_lrc, p->d_copies, ctx->d_fdesc_win, ctx->d_logcopy, g_base,
+                                                                      d_valid, d_logistic, d_x, p->pf_stride);
     mg_time_end(ctx);
     CUDA_TRY(ctx, cudaGetLastError());
     return MG_OK;

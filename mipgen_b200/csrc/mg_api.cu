@@ -102,16 +102,21 @@ static void emit_block(std::vector<uint32_t> &fd, int part, int depth, int slot_
     fd.push_back(fd_pack(FK_LEN, part, 0, 0, 0, 0));
 }
 
-static std::vector<uint32_t> build_feature_descriptors()
+static std::vector<uint32_t> build_feature_descriptors(bool window)
 {
+    // explicit front-end: per-warp count slots; window front-end: shared prefix-table rows
+    // (tri 0..63, di 64..79, mono 80..83, G+C 84 -- the same tables serve arms and insert)
     std::vector<uint32_t> fd;
-    emit_block(fd, 0, 2, 0, SLOT_EXT_DI, SLOT_EXT_MONO, SLOT_EXT_GC);                 // 1..22
-    for (int j = 0; j < MG_NLRC; j++) fd.push_back(fd_pack(FK_LRC, 0, 0, 0, 0, j));    // 23..66
-    emit_block(fd, 1, 3, SLOT_INS_TRI, SLOT_INS_DI, SLOT_INS_MONO, SLOT_INS_GC);      // 67..152
-    emit_block(fd, 2, 2, 0, SLOT_LIG_DI, SLOT_LIG_MONO, SLOT_LIG_GC);                 // 153..174
-    for (int j = 0; j < 16; j++) fd.push_back(fd_pack(FK_JUNC, 2, 0, 0, 0, j));        // 175..190
-    fd.push_back(fd_pack(FK_COPY, 0, 0, 0, 0, 0));                                     // 191
-    fd.push_back(fd_pack(FK_COPY, 2, 0, 0, 0, 1));                                     // 192
+    if (window) emit_block(fd, 0, 2, 0, 64, 80, 84);
+    else emit_block(fd, 0, 2, 0, SLOT_EXT_DI, SLOT_EXT_MONO, SLOT_EXT_GC);                      // 1..22
+    for (int j = 0; j < MG_NLRC; j++) fd.push_back(fd_pack(FK_LRC, 0, 0, 0, 0, j));              // 23..66
+    if (window) emit_block(fd, 1, 3, 0, 64, 80, 84);
+    else emit_block(fd, 1, 3, SLOT_INS_TRI, SLOT_INS_DI, SLOT_INS_MONO, SLOT_INS_GC);           // 67..152
+    if (window) emit_block(fd, 2, 2, 0, 64, 80, 84);
+    else emit_block(fd, 2, 2, 0, SLOT_LIG_DI, SLOT_LIG_MONO, SLOT_LIG_GC);                      // 153..174
+    for (int j = 0; j < 16; j++) fd.push_back(fd_pack(FK_JUNC, 2, 0, 0, 0, j));                  // 175..190
+    fd.push_back(fd_pack(FK_COPY, 0, 0, 0, 0, 0));                                               // 191
+    fd.push_back(fd_pack(FK_COPY, 2, 0, 0, 0, 1));                                               // 192
     return fd;
 }
 
@@ -152,10 +157,12 @@ extern "C" int mg_create(int device, mg_ctx **out)
     ctx->sm_count = prop.multiProcessorCount;
     if ((e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking)) != cudaSuccess) return fail("cudaStreamCreate", e);
 
-    std::vector<uint32_t> fd = build_feature_descriptors();
-    if (fd.size() != MG_NFEAT) { g_create_err = "internal: feature table size"; delete ctx; return MG_ERR_INVALID; }
+    std::vector<uint32_t> fd = build_feature_descriptors(false), fdw = build_feature_descriptors(true);
+    if (fd.size() != MG_NFEAT || fdw.size() != MG_NFEAT) { g_create_err = "internal: feature table size"; delete ctx; return MG_ERR_INVALID; }
     if ((e = cudaMalloc(&ctx->d_fdesc, MG_NFEAT * sizeof(uint32_t))) != cudaSuccess) return fail("cudaMalloc", e);
+    if ((e = cudaMalloc(&ctx->d_fdesc_win, MG_NFEAT * sizeof(uint32_t))) != cudaSuccess) return fail("cudaMalloc", e);
     cudaMemcpy(ctx->d_fdesc, fd.data(), MG_NFEAT * sizeof(uint32_t), cudaMemcpyHostToDevice);
+    cudaMemcpy(ctx->d_fdesc_win, fdw.data(), MG_NFEAT * sizeof(uint32_t), cudaMemcpyHostToDevice);
     // log10 of copy numbers 0..100 from the host libm, so features 191/192 are bit-identical to glibc
     double logtab[102];
     for (int i = 0; i <= 100; i++) logtab[i] = log10((double)i);
@@ -170,7 +177,7 @@ extern "C" int mg_create(int device, mg_ctx **out)
         lk[i] = (uint8_t)k;
         lc[i] = (uint8_t)code;
     }
-    if (mg_upload_lrc_tables(ctx, lk, lc) != MG_OK || launch_svr_setup(ctx) != MG_OK) {
+    if (mg_upload_lrc_tables(ctx, lk, lc) != MG_OK || launch_svr_setup(ctx) != MG_OK || launch_feat_setup(ctx) != MG_OK) {
         g_create_err = ctx->err;
         delete ctx;
         return MG_ERR_CUDA;
@@ -195,7 +202,7 @@ extern "C" void mg_destroy(mg_ctx *ctx)
     for (auto e : ctx->ev_free) cudaEventDestroy(e);
     if (ctx->sw_a) { cudaEventDestroy(ctx->sw_a); cudaEventDestroy(ctx->sw_b); }
     free_model(ctx);
-    cudaFree(ctx->d_x); cudaFree(ctx->d_fdesc); cudaFree(ctx->d_logcopy); cudaFree(ctx->d_cfg);
+    cudaFree(ctx->d_x); cudaFree(ctx->d_fdesc); cudaFree(ctx->d_fdesc_win); cudaFree(ctx->d_logcopy); cudaFree(ctx->d_cfg);
     cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
@@ -286,7 +293,15 @@ extern "C" int mg_set_config(mg_ctx *ctx, const mg_config *c)
     d->max_capture = h.max_capture; d->min_capture = h.min_capture; d->inc = h.inc; d->max_mip_overlap = h.max_mip_overlap;
     d->n_cap = h.n_cap; d->n_pairs = c->n_pairs; d->max_sum = h.max_sum; d->min_sum = h.min_sum;
     d->n_oligo = (int)h.oligo_sizes.size();
-    for (int i = 0; i < c->n_pairs; i++) { d->ext_len[i] = h.ext_len[i]; d->lig_len[i] = h.lig_len[i]; }
+    d->max_arm = 0;
+    d->min_arm = 1 << 30;
+    for (int i = 0; i < c->n_pairs; i++) {
+        d->ext_len[i] = h.ext_len[i]; d->lig_len[i] = h.lig_len[i];
+        d->max_arm = std::max(d->max_arm, std::max(h.ext_len[i], h.lig_len[i]));
+        d->min_arm = std::min(d->min_arm, std::min(h.ext_len[i], h.lig_len[i]));
+    }
+    h.max_arm = d->max_arm;
+    h.min_arm = d->min_arm;
     for (size_t i = 0; i < h.oligo_sizes.size(); i++) d->oligo_sizes[i] = h.oligo_sizes[i];
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
@@ -601,7 +616,7 @@ extern "C" void mg_panel_destroy(mg_panel *p)
     if (!p) return;
     cudaSetDevice(p->ctx->device);
     cudaStreamSynchronize(p->ctx->stream);
-    cudaFree(p->d_regions); cudaFree(p->d_codes); cudaFree(p->d_lrc); cudaFree(p->d_copies);
+    cudaFree(p->d_regions); cudaFree(p->d_tasks); cudaFree(p->d_codes); cudaFree(p->d_lrc); cudaFree(p->d_copies);
     cudaFree(p->d_valid); cudaFree(p->d_logistic); cudaFree(p->d_svr); cudaFree(p->d_feat);
     delete p;
 }
@@ -645,6 +660,26 @@ extern "C" int mg_panel_create(mg_ctx *ctx, const mg_region *regions, int n, mg_
     }
     p->n_cand = p->offsets[n];
     p->n_codes = codes;
+    // K-feat work items: windows of W consecutive scan starts; W grows with the panel so that
+    // there are several windows per SM but the per-window prefix tables stay well amortised
+    {
+        int64_t total_scan = 0;
+        for (int i = 0; i < n; i++) total_scan += p->h_regions[i].n_scan;
+        int W = (int)std::min<int64_t>(64, std::max<int64_t>(8, total_scan / ((int64_t)ctx->sm_count * 6)));
+        const int64_t per_scan = (int64_t)ctx->cfg.n_cap * (int64_t)ctx->cfg.ext_len.size() * 2;
+        while (W > 1 && W * per_scan > (1 << 24)) W /= 2;  // keep a window's candidate count in int range
+        for (int i = 0; i < n; i++)
+            for (int si = 0; si < p->h_regions[i].n_scan; si += W) {
+                DevTask t;
+                t.region = i; t.si0 = si; t.nsi = std::min(W, p->h_regions[i].n_scan - si); t.pad = 0;
+                t.g0 = p->h_regions[i].grid_off + (int64_t)si * per_scan;
+                p->h_tasks.push_back(t);
+            }
+        p->span_cap = W + ctx->cfg.max_arm + ctx->cfg.max_capture - ctx->cfg.min_arm + 4;
+        int words = (p->span_cap + 2) / 2;
+        if (words % 2 == 0) words++;  // odd word stride: table rows spread over the banks
+        p->pf_stride = 2 * words;
+    }
 #define P_TRY(expr) do { cudaError_t _e = (expr); if (_e != cudaSuccess) { ctx->err = std::string(#expr) + ": " + cudaGetErrorString(_e); mg_panel_destroy(p); return MG_ERR_CUDA; } } while (0)
     if (n > 0) {
         std::vector<char> ascii((size_t)codes);
@@ -662,6 +697,10 @@ extern "C" int mg_panel_create(mg_ctx *ctx, const mg_region *regions, int n, mg_
         P_TRY(cudaMalloc(&p->d_regions, (size_t)n * sizeof(DevRegion)));
         P_TRY(cudaMemcpyAsync(d_ascii, ascii.data(), (size_t)codes, cudaMemcpyHostToDevice, ctx->stream));
         P_TRY(cudaMemcpyAsync(p->d_regions, p->h_regions.data(), (size_t)n * sizeof(DevRegion), cudaMemcpyHostToDevice, ctx->stream));
+        if (!p->h_tasks.empty()) {
+            P_TRY(cudaMalloc(&p->d_tasks, p->h_tasks.size() * sizeof(DevTask)));
+            P_TRY(cudaMemcpyAsync(p->d_tasks, p->h_tasks.data(), p->h_tasks.size() * sizeof(DevTask), cudaMemcpyHostToDevice, ctx->stream));
+        }
         if (any_lrc) {
             P_TRY(cudaMalloc(&p->d_lrc, lrc.size() * 8));
             P_TRY(cudaMemcpyAsync(p->d_lrc, lrc.data(), lrc.size() * 8, cudaMemcpyHostToDevice, ctx->stream));
@@ -700,18 +739,25 @@ extern "C" int mg_panel_score(mg_ctx *ctx, mg_panel *p, int want)
         CUDA_TRY(ctx, cudaMemsetAsync(p->d_feat, 0, (size_t)rows * MG_NFEAT * 8, ctx->stream));
     }
     int rc = MG_OK;
+    const int n_tasks = (int)p->h_tasks.size();
     if (!w_svr && !w_feat) {
-        rc = launch_feat_grid(ctx, p, 0, p->n_cand, p->d_valid, w_log ? p->d_logistic : nullptr, nullptr);
+        rc = launch_feat_grid(ctx, p, 0, n_tasks, 0, p->n_cand, p->d_valid, w_log ? p->d_logistic : nullptr, nullptr);
     } else if (w_feat) {
-        rc = launch_feat_grid(ctx, p, 0, p->n_cand, p->d_valid, w_log ? p->d_logistic : nullptr, p->d_feat);
+        rc = launch_feat_grid(ctx, p, 0, n_tasks, 0, p->n_cand, p->d_valid, w_log ? p->d_logistic : nullptr, p->d_feat);
         if (rc == MG_OK && w_svr) rc = launch_svr(ctx, p->d_feat, p->n_cand, p->d_valid, p->d_svr);
     } else {
-        const int64_t chunk = std::min<int64_t>(kMaxChunkRows, p->n_cand);
-        if ((rc = ensure_x(ctx, chunk)) != MG_OK) return rc;
-        for (int64_t g0 = 0; g0 < p->n_cand && rc == MG_OK; g0 += chunk) {
-            const int64_t g1 = std::min(p->n_cand, g0 + chunk);
-            rc = launch_feat_grid(ctx, p, g0, g1, p->d_valid, w_log ? p->d_logistic : nullptr, ctx->d_x);
+        // feature rows live only in a workspace: walk the panel in chunks of whole windows
+        int t0 = 0;
+        while (t0 < n_tasks && rc == MG_OK) {
+            const int64_t g0 = p->h_tasks[t0].g0;
+            int t1 = t0 + 1;
+            auto end_of = [&](int t) { return t < n_tasks ? p->h_tasks[t].g0 : p->n_cand; };
+            while (t1 < n_tasks && end_of(t1 + 1) - g0 <= kMaxChunkRows) t1++;
+            const int64_t g1 = end_of(t1);
+            if ((rc = ensure_x(ctx, g1 - g0)) != MG_OK) return rc;
+            rc = launch_feat_grid(ctx, p, t0, t1, g0, g1 - g0, p->d_valid, w_log ? p->d_logistic : nullptr, ctx->d_x);
             if (rc == MG_OK) rc = launch_svr(ctx, ctx->d_x, g1 - g0, p->d_valid + g0, p->d_svr + g0);
+            t0 = t1;
         }
     }
     if (rc == MG_OK) {

@@ -23,7 +23,7 @@ enum : uint8_t { B_A = 0, B_C = 1, B_G = 2, B_T = 3, B_N = 4, B_DASH = 5, B_OTHE
 struct DevConfig {
     int max_capture, min_capture, inc, max_mip_overlap;
     int n_cap, n_pairs, max_sum, min_sum;
-    int n_oligo;
+    int n_oligo, max_arm, min_arm, pad0;
     int ext_len[MG_MAX_PAIRS];
     int lig_len[MG_MAX_PAIRS];
     int oligo_sizes[MG_MAX_OLIGO];
@@ -37,6 +37,14 @@ struct DevRegion {
     int seq_len, seq_start, seq_stop;
     int start_flanked, stop_flanked;
     int first_scan, n_scan;
+    int pad;
+};
+
+// one K-feat work item: a window of consecutive scan starts of one region
+struct DevTask {
+    int64_t g0;      // global candidate index of the window's first grid point
+    int region;      // index into DevRegion[]
+    int si0, nsi;    // first scan index of the window, number of scan starts
     int pad;
 };
 
@@ -100,7 +108,7 @@ __host__ __device__ inline uint32_t fd_pack(uint32_t kind, uint32_t part, uint32
 struct HostConfig {
     int max_capture = 0, min_capture = 0, inc = 1, max_mip_overlap = 0;
     std::vector<int> ext_len, lig_len, oligo_sizes;
-    int n_cap = 0, max_sum = 0, min_sum = 0;
+    int n_cap = 0, max_sum = 0, min_sum = 0, max_arm = 0, min_arm = 0;
 };
 
 struct EventPair { cudaEvent_t a, b; int which; long units; };
@@ -114,7 +122,8 @@ struct mg_ctx {
     HostConfig cfg;
     DevConfig *d_cfg = nullptr;
     // tables
-    uint32_t *d_fdesc = nullptr;    // [192] packed feature descriptors
+    uint32_t *d_fdesc = nullptr;    // [192] packed feature descriptors (explicit front-end: count slots)
+    uint32_t *d_fdesc_win = nullptr;  // [192] the same with prefix-table rows (window front-end)
     double *d_logcopy = nullptr;    // [102] log10(copy) for copy 0..100 (glibc), [101] = 2.0
     // model
     bool has_model = false;
@@ -144,6 +153,9 @@ struct mg_panel {
     std::vector<int64_t> offsets;  // n+1
     std::vector<DevRegion> h_regions;
     DevRegion *d_regions = nullptr;
+    std::vector<DevTask> h_tasks;  // K-feat windows, ascending in g0
+    DevTask *d_tasks = nullptr;
+    int span_cap = 0, pf_stride = 0;
     uint8_t *d_codes = nullptr;
     int64_t n_codes = 0;
     double *d_lrc = nullptr;       // [n_regions][44]
@@ -171,10 +183,11 @@ int mg_time_end(mg_ctx *ctx);
 
 int launch_encode(mg_ctx *ctx, const char *d_ascii, uint8_t *d_codes, int64_t n);
 int launch_lrc(mg_ctx *ctx, const uint8_t *d_codes, int n, int denom, double *d_out44);
-// grid front-end: candidates [g0, g1) of the panel; any of valid/logistic/x may be null.
-// x rows are written at row (g - g0).
-int launch_feat_grid(mg_ctx *ctx, const mg_panel *p, int64_t g0, int64_t g1, uint8_t *d_valid,
+// grid front-end: any of valid/logistic/x may be null; x rows are written at row (g - g_base).
+// tasks [task0, task1) hold n_cand consecutive candidates starting at global index g_base
+int launch_feat_grid(mg_ctx *ctx, const mg_panel *p, int task0, int task1, int64_t g_base, int64_t n_cand, uint8_t *d_valid,
                      double *d_logistic, double *d_x);
+int launch_feat_setup(mg_ctx *ctx);
 // explicit front-end
 int launch_feat_explicit(mg_ctx *ctx, const DevCand *d_cands, const uint8_t *d_codes, const double *d_lrc,
                          int64_t n, double *d_logistic, double *d_x);
