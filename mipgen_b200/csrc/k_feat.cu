@@ -220,7 +220,7 @@ __device__ __forceinline__ void warp_candidate(const View &v, int *sm, int lane,
 }
 
 // The logistic model, one thread per candidate (SVMipv4.cpp:142-247).
-__device__ __forceinline__ double logistic_score(const Stash &s, const double *__restrict__ logtab)
+__device__ __noinline__ double logistic_score(const Stash &s, const double *__restrict__ logtab)
 {
     if (s.state == 0) return __longlong_as_double(0x7ff8000000000000LL);
     if (s.state == 1) return -1000.0;
@@ -265,8 +265,11 @@ __device__ __forceinline__ double logistic_score(const Stash &s, const double *_
 
 // ------------------------------- grid front-end -------------------------------
 // prefix-table rows
-constexpr int PF_TRI = 0, PF_DI = 64, PF_MONO = 80, PF_GC = 84, PF_NDASH = 85, PF_OTHER = 86, PF_TRANS = 87, PF_ROWS = 88;
+constexpr int PF_DI = 64, PF_MONO = 80, PF_GC = 84, PF_NDASH = 85, PF_OTHER = 86, PF_TRANS = 87, PF_ROWS = 88;
 constexpr int kRecipN = 512;
+// per-warp candidate records (field-major, 32 candidates): 11 ints + 2 doubles
+enum { GW_FLAGS = 0, GW_JCODE, GW_EXT_A, GW_EXT_N, GW_EXT_LEN, GW_LIG_A, GW_LIG_N, GW_LIG_LEN, GW_TGT_A, GW_TGT_N, GW_SCAN, GW_PAD,
+       GW_LCE = 12, GW_LCL = 14, GW_FIELDS = 16 };
 
 struct WinSmem {
     const uint16_t *P;   // [PF_ROWS][stride]
@@ -286,17 +289,6 @@ __device__ __forceinline__ int pf_count(const WinSmem &w, int row, int a, int n,
     return (int)(uint16_t)(r[end] - r[a]);
 }
 
-__device__ __forceinline__ double small_div(const WinSmem &w, int c, int n)
-{
-    if (n > 0 && n < kRecipN) {
-        const double a = (double)c, b = (double)n, y = w.rn[n];
-        const double q0 = __dmul_rn(a, y);
-        const double r = __fma_rn(-q0, b, a);
-        return __fma_rn(r, y, q0);
-    }
-    return __ddiv_rn((double)c, (double)n);
-}
-
 struct Geo {
     int ok;                        // passes the static skips and lies inside the sequence
     int rc;                        // strand
@@ -306,23 +298,26 @@ struct Geo {
     int ext_start, lig_start;      // chromosome coordinates (copy look-up)
 };
 
-__device__ __forceinline__ Geo decode_candidate(const DevConfig *__restrict__ cfg, const DevRegion &r, int span0, int si, int rem)
+struct WinCfg {  // per-kernel constants, read once
+    int max_capture, min_capture, inc, max_mip_overlap, n_cap, n_pairs;
+    const int *pair_e, *pair_l;  // shared-memory copies of the arm-pair table
+};
+
+// geometry of grid point (scan index si, capture index ci, pair p, strand) -- no divisions
+__device__ __forceinline__ Geo candidate_geometry(const WinCfg &c, const DevRegion &r, int span0, int si, int ci, int p, int strand)
 {
     Geo g;
-    const int n_pairs = cfg->n_pairs, inc = cfg->inc;
-    g.rc = rem & 1;
-    rem >>= 1;
-    const int ci = rem / n_pairs, p = rem - ci * n_pairs;
-    const int s = r.first_scan + si, cap = cfg->max_capture - ci * inc;
-    const int e = cfg->ext_len[p], l = cfg->lig_len[p];
+    g.rc = strand;
+    const int s = r.first_scan + si, cap = c.max_capture - ci * c.inc;
+    const int e = c.pair_e[p], l = c.pair_l[p];
     // static skips: mipgen.cpp:429, 443, 444
-    bool ok = !(cap > r.stop_flanked - r.start_flanked + cfg->max_mip_overlap && cap - inc >= cfg->min_capture);
+    bool ok = !(cap > r.stop_flanked - r.start_flanked + c.max_mip_overlap && cap - c.inc >= c.min_capture);
     ok = ok && !(s - e <= 0 || s - l <= 0);
     ok = ok && !(s + cap - e - 1 > r.seq_stop || s + cap - l - 1 > r.seq_stop);
     const int t = s + cap - (e + l) - 1;  // scan_stop (:449)
     g.ext_len = e; g.lig_len = l; g.scan_size = t - s + 1;
-    g.ext_start = g.rc ? t + 1 : s - e;   // Plus/MinusSVMipv4 ctors
-    g.lig_start = g.rc ? s - l : t + 1;
+    g.ext_start = strand ? t + 1 : s - e;   // Plus/MinusSVMipv4 ctors
+    g.lig_start = strand ? s - l : t + 1;
     const int eo = g.ext_start - r.seq_start, lo = g.lig_start - r.seq_start, to = s - r.seq_start;
     // std::string::substr(off,len) throws for off > size; it clamps the length otherwise
     ok = ok && eo >= 0 && lo >= 0 && to >= 0 && eo <= r.seq_len && lo <= r.seq_len && to <= r.seq_len && g.scan_size >= 0;
@@ -364,7 +359,10 @@ k_feat_window(const DevConfig *__restrict__ cfg, const DevRegion *__restrict__ r
     extern __shared__ __align__(16) uint8_t smem_raw[];
     double *rn = reinterpret_cast<double *>(smem_raw);            // [kRecipN]
     double *lrc_s = rn + kRecipN;                                  // [44]
-    uint16_t *P = reinterpret_cast<uint16_t *>(lrc_s + MG_NLRC);   // [PF_ROWS][stride]
+    int *geo_s = reinterpret_cast<int *>(lrc_s + MG_NLRC);         // [warps][GW_FIELDS][32]
+    int *pair_e = geo_s + kWarpsPerBlock * GW_FIELDS * 32;         // [n_pairs]
+    int *pair_l = pair_e + cfg->n_pairs;                           // [n_pairs]
+    uint16_t *P = reinterpret_cast<uint16_t *>(pair_l + cfg->n_pairs + (cfg->n_pairs & 1) * 2);   // [PF_ROWS][stride]
     uint8_t *codes_s = reinterpret_cast<uint8_t *>(P + PF_ROWS * stride);
 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -372,8 +370,16 @@ k_feat_window(const DevConfig *__restrict__ cfg, const DevRegion *__restrict__ r
 #pragma unroll
     for (int m = 0; m < 6; m++) fd[m] = fdesc[lane + 32 * m];
     for (int i = threadIdx.x; i < kRecipN; i += blockDim.x) rn[i] = i ? __ddiv_rn(1.0, (double)i) : 0.0;
+    for (int i = threadIdx.x; i < cfg->n_pairs; i += blockDim.x) { pair_e[i] = cfg->ext_len[i]; pair_l[i] = cfg->lig_len[i]; }
+    WinCfg wc;
+    wc.max_capture = cfg->max_capture; wc.min_capture = cfg->min_capture; wc.inc = cfg->inc; wc.max_mip_overlap = cfg->max_mip_overlap;
+    wc.n_cap = cfg->n_cap; wc.n_pairs = cfg->n_pairs; wc.pair_e = pair_e; wc.pair_l = pair_l;
+    // per-lane feature constants: table-row offsets for both strands
+    int rowoff_f[6], rowoff_r[6];
+#pragma unroll
+    for (int m = 0; m < 6; m++) { rowoff_f[m] = (int)((fd[m] >> 7) & 255) * stride; rowoff_r[m] = (int)((fd[m] >> 15) & 255) * stride; }
 
-    const int per_scan = cfg->n_cap * cfg->n_pairs * 2;
+    const int per_scan = wc.n_cap * wc.n_pairs * 2;
     const int max_arm = cfg->max_arm, min_arm = cfg->min_arm;
 
     for (int ti = task0 + blockIdx.x; ti < task1; ti += gridDim.x) {
@@ -390,119 +396,187 @@ k_feat_window(const DevConfig *__restrict__ cfg, const DevRegion *__restrict__ r
         for (int i = threadIdx.x; i < span_len + 3; i += blockDim.x) codes_s[i] = i < span_len ? codes[r.seq_off + span0 + i] : (uint8_t)B_NONE;
         if (threadIdx.x < MG_NLRC) lrc_s[threadIdx.x] = lrc_all ? lrc_all[(int64_t)tk.region * MG_NLRC + threadIdx.x] : 0.0;
         __syncthreads();
-        if (threadIdx.x < PF_ROWS) {
-            const int row = threadIdx.x;
-            uint16_t *pr = P + row * stride;
-            uint32_t cnt = 0;
-            pr[0] = 0;
-            uint32_t cm = B_NONE, c0 = codes_s[0], c1 = codes_s[1], c2 = codes_s[2];
-            for (int p = 0; p < span_len; p++) {
-                bool hit;
-                if (row < PF_DI) hit = c0 < 4 && c1 < 4 && c2 < 4 && (int)(c0 * 16 + c1 * 4 + c2) == row;
-                else if (row < PF_MONO) hit = c0 < 4 && c1 < 4 && (int)(c0 * 4 + c1) == row - PF_DI;
-                else if (row < PF_GC) hit = (int)c0 == row - PF_MONO;
-                else if (row == PF_GC) hit = c0 == B_C || c0 == B_G;
-                else if (row == PF_NDASH) hit = c0 == B_N || c0 == B_DASH;
-                else if (row == PF_OTHER) hit = c0 >= 4;
-                else hit = p > 0 && base_class(c0) != base_class(cm);
-                cnt += hit;
-                pr[p + 1] = (uint16_t)cnt;
-                cm = c0; c0 = c1; c1 = c2; c2 = codes_s[p + 3];
+        // prefix tables: warp w owns rows w, w+8, ...; 32 positions at a time, the running
+        // count of a row is carry + popc(ballot(hit) & lanes-below-or-equal)
+        {
+            uint32_t carry[(PF_ROWS + kWarpsPerBlock - 1) / kWarpsPerBlock];
+#pragma unroll
+            for (int i = 0; i < (PF_ROWS + kWarpsPerBlock - 1) / kWarpsPerBlock; i++) carry[i] = 0;
+            if (lane == 0)
+                for (int row = warp; row < PF_ROWS; row += kWarpsPerBlock) P[row * stride] = 0;
+            const uint32_t le_mask = 0xffffffffu >> (31 - lane);
+            for (int p0 = 0; p0 < span_len; p0 += 32) {
+                const int p = p0 + lane;
+                const bool in = p < span_len;
+                const uint32_t c0 = in ? codes_s[p] : (uint32_t)B_NONE, c1 = in ? codes_s[p + 1] : (uint32_t)B_NONE,
+                               c2 = in ? codes_s[p + 2] : (uint32_t)B_NONE, cm = p > 0 && in ? codes_s[p - 1] : (uint32_t)B_NONE;
+                const int tri = (c0 < 4 && c1 < 4 && c2 < 4) ? (int)(c0 * 16 + c1 * 4 + c2) : -1;
+                const int di = (c0 < 4 && c1 < 4) ? (int)(c0 * 4 + c1) : -1;
+#pragma unroll
+                for (int i = 0; i < (PF_ROWS + kWarpsPerBlock - 1) / kWarpsPerBlock; i++) {
+                    const int row = warp + i * kWarpsPerBlock;
+                    if (row < PF_ROWS) {
+                        bool hit;
+                        if (row < PF_DI) hit = tri == row;
+                        else if (row < PF_MONO) hit = di == row - PF_DI;
+                        else if (row < PF_GC) hit = (int)c0 == row - PF_MONO;
+                        else if (row == PF_GC) hit = c0 == B_C || c0 == B_G;
+                        else if (row == PF_NDASH) hit = c0 == B_N || c0 == B_DASH;
+                        else if (row == PF_OTHER) hit = c0 >= 4 && in;
+                        else hit = p > 0 && in && base_class(c0) != base_class(cm);
+                        const uint32_t m = __ballot_sync(0xffffffffu, hit);
+                        if (in) P[row * stride + p + 1] = (uint16_t)(carry[i] + __popc(m & le_mask));
+                        carry[i] += __popc(m);
+                    }
+                }
             }
         }
         __syncthreads();
 
+        // long-range content values this lane writes in groups 0, 1, 2 (constant for the whole window)
+        const double lrc_r0 = lane >= 22 ? lrc_s[lane - 22] : 0.0, lrc_r1 = lrc_s[10 + lane], lrc_r2 = lane < 2 ? lrc_s[42 + lane] : 0.0;
         WinSmem w;
         w.P = P; w.stride = stride; w.codes = codes_s; w.rn = rn; w.lrc = lrc_s; w.span_len = span_len;
         const int n_c = tk.nsi * per_scan;
+        int *gw = geo_s + warp * (GW_FIELDS * 32);  // this warp's candidate records, field-major
         for (int blk = warp; blk * 32 < n_c; blk += kWarpsPerBlock) {
-            // ---- feature rows: the warp writes candidate after candidate ----
-            if (x) {
-                const int jend = min(32, n_c - blk * 32);
-                for (int c = 0; c < jend; c++) {
-                    const int j = blk * 32 + c;
-                    const int si = j / per_scan;
-                    const Geo g = decode_candidate(cfg, r, span0, tk.si0 + si, j - si * per_scan);
-                    double *xrow = x + (tk.g0 + j - g_base) * MG_NFEAT;
-                    bool zero = !g.ok;
-                    int ext_copy = 1, lig_copy = 1, jcode = -1;
-                    if (g.ok) {
-                        // 'N' in an arm, or '-' in mip_seq (== '-' in an arm)   SVMipv4.cpp:63-68 -> 192 zeros
-                        zero = pf_count(w, PF_NDASH, g.ext_a, g.ext_n, 1) + pf_count(w, PF_NDASH, g.lig_a, g.lig_n, 1) > 0;
-                        jcode = junction_code(w, g);
-                        if (r.copy_off >= 0) {
-                            ext_copy = copy_lookup(cfg, r, copies, g.ext_start, g.ext_len);
-                            lig_copy = copy_lookup(cfg, r, copies, g.lig_start, g.lig_len);
-                        }
+            // ---- phase 1: lane c works out candidate c (geometry, validity, junction, copies, logistic) ----
+            const int j = blk * 32 + lane;
+            Geo g;
+            g.ok = 0;
+            int flags = 0, jcode = -1;
+            double lce = 0.0, lcl = 0.0;  // log10(1)
+            if (j < n_c) {
+                const int si = j / per_scan;
+                const int rem = j - si * per_scan;
+                const int ci = (rem >> 1) / wc.n_pairs;
+                g = candidate_geometry(wc, r, span0, tk.si0 + si, ci, (rem >> 1) - ci * wc.n_pairs, rem & 1);
+                int ext_copy = 1, lig_copy = 1;
+                bool invalid = false;
+                if (g.ok) {
+                    // 'N' in an arm, or '-' in mip_seq (== '-' in an arm)   SVMipv4.cpp:63-68, 116
+                    invalid = pf_count(w, PF_NDASH, g.ext_a, g.ext_n, 1) + pf_count(w, PF_NDASH, g.lig_a, g.lig_n, 1) > 0;
+                    jcode = junction_code(w, g);
+                    if (r.copy_off >= 0) {
+                        ext_copy = copy_lookup(cfg, r, copies, g.ext_start, g.ext_len);
+                        lig_copy = copy_lookup(cfg, r, copies, g.lig_start, g.lig_len);
+                        lce = log_copy(ext_copy, logtab);
+                        lcl = log_copy(lig_copy, logtab);
                     }
+                    // every divisor len-2 .. len inside the reciprocal table?
+                    const bool fast = g.ext_len > 2 && g.lig_len > 2 && g.scan_size > 3 && g.ext_len < kRecipN && g.lig_len < kRecipN &&
+                                      g.scan_size < kRecipN;
+                    flags = 1 | (invalid ? 2 : 0) | (fast ? 4 : 0) | (g.rc ? 8 : 0);
+                }
+                if (valid) valid[tk.g0 + j] = (uint8_t)g.ok;
+                if (logistic) {
+                    Stash st;
+                    st.state = !g.ok ? 0 : (invalid ? 1 : 2);
+                    if (st.state == 2) {
+                        const int G = PF_MONO + (g.rc ? B_C : B_G), Cc = PF_MONO + (g.rc ? B_G : B_C), A = PF_MONO + (g.rc ? B_T : B_A);
+                        st.eg = pf_count(w, G, g.ext_a, g.ext_n, 1); st.ec = pf_count(w, Cc, g.ext_a, g.ext_n, 1); st.ea = pf_count(w, A, g.ext_a, g.ext_n, 1);
+                        st.lg = pf_count(w, G, g.lig_a, g.lig_n, 1); st.lc = pf_count(w, Cc, g.lig_a, g.lig_n, 1); st.la = pf_count(w, A, g.lig_a, g.lig_n, 1);
+                        st.tg = pf_count(w, G, g.tgt_a, g.tgt_n, 1); st.tc = pf_count(w, Cc, g.tgt_a, g.tgt_n, 1); st.ta = pf_count(w, A, g.tgt_a, g.tgt_n, 1);
+                        // run count (SVMipv4.cpp:118-141)
+                        const int nt = min(g.tgt_n, g.scan_size);
+                        int runs;
+                        if (pf_count(w, PF_OTHER, g.tgt_a, nt, 1) == 0) {
+                            const uint16_t *tr = P + PF_TRANS * stride;
+                            runs = 1 + (nt >= 2 ? (int)(uint16_t)(tr[g.tgt_a + nt] - tr[g.tgt_a + 1]) : 0);
+                        } else {
+                            // characters outside ACGT make the reference's state machine order dependent:
+                            // replay it literally, in stored-string order (rare path)
+                            int rr = 0;
+                            if (nt > 0) {
+                                int last = base_class(g.rc ? codes_s[g.tgt_a + g.tgt_n - 1] : codes_s[g.tgt_a]);
+                                for (int i = 1; i < nt; i++) {
+                                    const int cur = base_class(g.rc ? codes_s[g.tgt_a + g.tgt_n - 1 - i] : codes_s[g.tgt_a + i]);
+                                    if (cur == 0) { if (last != 0) { rr++; last = 0; } }
+                                    else { if (last != 1) { rr++; last = cur; } }
+                                }
+                            }
+                            runs = rr + 1;
+                        }
+                        st.runs = runs; st.ext_len = g.ext_len; st.lig_len = g.lig_len; st.scan_size = g.scan_size;
+                        st.jcode = jcode; st.ext_copy = ext_copy; st.lig_copy = lig_copy;
+                    }
+                    logistic[tk.g0 + j] = logistic_score(st, logtab);
+                }
+            }
+            if (!x) continue;
+
+            // ---- phase 2: the warp writes the 32 feature rows, reading each record by broadcast ----
+            __syncwarp();
+            gw[GW_FLAGS * 32 + lane] = flags; gw[GW_JCODE * 32 + lane] = jcode;
+            gw[GW_EXT_A * 32 + lane] = g.ext_a; gw[GW_EXT_N * 32 + lane] = g.ext_n; gw[GW_EXT_LEN * 32 + lane] = g.ext_len;
+            gw[GW_LIG_A * 32 + lane] = g.lig_a; gw[GW_LIG_N * 32 + lane] = g.lig_n; gw[GW_LIG_LEN * 32 + lane] = g.lig_len;
+            gw[GW_TGT_A * 32 + lane] = g.tgt_a; gw[GW_TGT_N * 32 + lane] = g.tgt_n; gw[GW_SCAN * 32 + lane] = g.scan_size;
+            reinterpret_cast<double *>(gw + GW_LCE * 32)[lane] = lce;
+            reinterpret_cast<double *>(gw + GW_LCL * 32)[lane] = lcl;
+            __syncwarp();
+            const int jend = min(32, n_c - blk * 32);
+            double *xrow = x + (tk.g0 + (int64_t)blk * 32 - g_base) * MG_NFEAT + lane;
+            for (int c = 0; c < jend; c++, xrow += MG_NFEAT) {
+                const int fl = gw[GW_FLAGS * 32 + c];
+                if (!(fl & 1) || (fl & 2)) {
+                    // statically skipped grid point (never read) or invalid candidate: 192 zeros
+#pragma unroll
+                    for (int m = 0; m < 6; m++) xrow[32 * m] = 0.0;
+                    continue;
+                }
+                const bool rc = fl & 8;
+                const int jc = gw[GW_JCODE * 32 + c];
+                const int ext_a = gw[GW_EXT_A * 32 + c], ext_n = gw[GW_EXT_N * 32 + c], ext_len = gw[GW_EXT_LEN * 32 + c];
+                const int lig_a = gw[GW_LIG_A * 32 + c], lig_n = gw[GW_LIG_N * 32 + c], lig_len = gw[GW_LIG_LEN * 32 + c];
+                const int tgt_a = gw[GW_TGT_A * 32 + c], tgt_n = gw[GW_TGT_N * 32 + c], scan_size = gw[GW_SCAN * 32 + c];
+                const double ce = reinterpret_cast<const double *>(gw + GW_LCE * 32)[c], cl = reinterpret_cast<const double *>(gw + GW_LCL * 32)[c];
+                if (fl & 4) {
+                    // The six 32-feature groups have a fixed structure (SVMipv4.cpp:72-112, checked against the
+                    // descriptor table at context creation):
+                    //   m=0: ext ratios 0..20 | ext_len 21 | lrc 22..31      m=1: lrc 32..63
+                    //   m=2: lrc 64,65 | insert ratios 66..95                  m=3: insert ratios 96..127
+                    //   m=4: insert ratios 128..150 | scan_size 151 | lig ratios 152..159
+                    //   m=5: lig ratios 160..172 | lig_len 173 | junction one-hot 174..189 | log copies 190,191
+                    auto ratio = [&](int m, int a, int n, int len) {
+                        const int km1 = (fd[m] >> 5) & 3;
+                        const int ro = rc ? rowoff_r[m] : rowoff_f[m];
+                        const int end = a + n - km1;
+                        const int cnt = (int)(uint16_t)(P[ro + max(end, a)] - P[ro + a]);
+                        const int den = len - km1;
+                        const double y = rn[den], ad = (double)cnt, bd = (double)den;
+                        const double q0 = __dmul_rn(ad, y);
+                        return __fma_rn(__fma_rn(-q0, bd, ad), y, q0);
+                    };
+                    double v0 = ratio(0, ext_a, ext_n, ext_len);
+                    v0 = lane < 21 ? v0 : (lane == 21 ? (double)ext_len : lrc_r0);
+                    double v2 = ratio(2, tgt_a, tgt_n, scan_size);
+                    v2 = lane < 2 ? lrc_r2 : v2;
+                    const double v3 = ratio(3, tgt_a, tgt_n, scan_size);
+                    const bool lig4 = lane >= 24;
+                    double v4 = ratio(4, lig4 ? lig_a : tgt_a, lig4 ? lig_n : tgt_n, lig4 ? lig_len : scan_size);
+                    v4 = lane == 23 ? (double)scan_size : v4;
+                    double v5 = ratio(5, lig_a, lig_n, lig_len);
+                    v5 = lane < 13 ? v5 : (lane == 13 ? (double)lig_len : (lane < 30 ? (jc == lane - 14 ? 1.0 : 0.0) : (lane == 30 ? ce : cl)));
+                    xrow[0] = v0; xrow[32] = lrc_r1; xrow[64] = v2; xrow[96] = v3; xrow[128] = v4; xrow[160] = v5;
+                } else {
+                    // unusual lengths (divisor <= 0 or beyond the reciprocal table): plain IEEE division
 #pragma unroll
                     for (int m = 0; m < 6; m++) {
                         const uint32_t d = fd[m];
                         const uint32_t kind = d & 7, part = (d >> 3) & 3, km1 = (d >> 5) & 3, jj = (d >> 23) & 255;
-                        const int len = part == 0 ? g.ext_len : (part == 1 ? g.scan_size : g.lig_len);
+                        const int len = part == 0 ? ext_len : (part == 1 ? scan_size : lig_len);
                         double val;
-                        if (zero) val = 0.0;
-                        else if (kind == FK_RATIO) {
-                            const int a = part == 0 ? g.ext_a : (part == 1 ? g.tgt_a : g.lig_a);
-                            const int n = part == 0 ? g.ext_n : (part == 1 ? g.tgt_n : g.lig_n);
-                            const int row = g.rc ? (int)((d >> 15) & 255) : (int)((d >> 7) & 255);
-                            const int k = row == PF_GC ? 1 : (int)km1 + 1;
-                            val = small_div(w, pf_count(w, row, a, n, k), len - (int)km1);
+                        if (kind == FK_RATIO) {
+                            const int a = part == 0 ? ext_a : (part == 1 ? tgt_a : lig_a);
+                            const int n = part == 0 ? ext_n : (part == 1 ? tgt_n : lig_n);
+                            const int row = rc ? (int)((d >> 15) & 255) : (int)((d >> 7) & 255);
+                            val = __ddiv_rn((double)pf_count(w, row, a, n, (int)km1 + 1), (double)(len - (int)km1));
                         } else if (kind == FK_LEN) val = (double)len;
                         else if (kind == FK_LRC) val = lrc_s[jj];
-                        else if (kind == FK_JUNC) val = (jcode == (int)jj) ? 1.0 : 0.0;
-                        else val = log_copy(jj == 0 ? ext_copy : lig_copy, logtab);
-                        xrow[lane + 32 * m] = val;
+                        else if (kind == FK_JUNC) val = (jc == (int)jj) ? 1.0 : 0.0;
+                        else val = jj == 0 ? ce : cl;
+                        xrow[32 * m] = val;
                     }
-                }
-            }
-            // ---- validity + logistic score: one lane per candidate ----
-            const int j = blk * 32 + lane;
-            if (j < n_c && (valid || logistic)) {
-                const int si = j / per_scan;
-                const Geo g = decode_candidate(cfg, r, span0, tk.si0 + si, j - si * per_scan);
-                if (valid) valid[tk.g0 + j] = (uint8_t)g.ok;
-                if (logistic) {
-                    Stash st;
-                    st.state = 0;
-                    if (g.ok) {
-                        const bool invalid = pf_count(w, PF_NDASH, g.ext_a, g.ext_n, 1) + pf_count(w, PF_NDASH, g.lig_a, g.lig_n, 1) > 0;
-                        st.state = invalid ? 1 : 2;
-                        if (!invalid) {
-                            const int G = PF_MONO + (g.rc ? B_C : B_G), Cc = PF_MONO + (g.rc ? B_G : B_C), A = PF_MONO + (g.rc ? B_T : B_A);
-                            st.eg = pf_count(w, G, g.ext_a, g.ext_n, 1); st.ec = pf_count(w, Cc, g.ext_a, g.ext_n, 1); st.ea = pf_count(w, A, g.ext_a, g.ext_n, 1);
-                            st.lg = pf_count(w, G, g.lig_a, g.lig_n, 1); st.lc = pf_count(w, Cc, g.lig_a, g.lig_n, 1); st.la = pf_count(w, A, g.lig_a, g.lig_n, 1);
-                            st.tg = pf_count(w, G, g.tgt_a, g.tgt_n, 1); st.tc = pf_count(w, Cc, g.tgt_a, g.tgt_n, 1); st.ta = pf_count(w, A, g.tgt_a, g.tgt_n, 1);
-                            // run count (SVMipv4.cpp:118-141)
-                            const int nt = min(g.tgt_n, g.scan_size);
-                            int runs;
-                            if (pf_count(w, PF_OTHER, g.tgt_a, nt, 1) == 0) {
-                                const uint16_t *tr = P + PF_TRANS * stride;
-                                runs = 1 + (nt >= 2 ? (int)(uint16_t)(tr[g.tgt_a + nt] - tr[g.tgt_a + 1]) : 0);
-                            } else {
-                                // characters outside ACGT make the reference's state machine order dependent:
-                                // replay it literally, in stored-string order (rare path)
-                                int rr = 0;
-                                if (nt > 0) {
-                                    int last = base_class(g.rc ? codes_s[g.tgt_a + g.tgt_n - 1] : codes_s[g.tgt_a]);
-                                    for (int i = 1; i < nt; i++) {
-                                        const int cur = base_class(g.rc ? codes_s[g.tgt_a + g.tgt_n - 1 - i] : codes_s[g.tgt_a + i]);
-                                        if (cur == 0) { if (last != 0) { rr++; last = 0; } }
-                                        else { if (last != 1) { rr++; last = cur; } }
-                                    }
-                                }
-                                runs = rr + 1;
-                            }
-                            st.runs = runs; st.ext_len = g.ext_len; st.lig_len = g.lig_len; st.scan_size = g.scan_size;
-                            st.jcode = junction_code(w, g);
-                            st.ext_copy = 1; st.lig_copy = 1;
-                            if (r.copy_off >= 0) {
-                                st.ext_copy = copy_lookup(cfg, r, copies, g.ext_start, g.ext_len);
-                                st.lig_copy = copy_lookup(cfg, r, copies, g.lig_start, g.lig_len);
-                            }
-                        }
-                    }
-                    logistic[tk.g0 + j] = logistic_score(st, logtab);
                 }
             }
         }
@@ -633,9 +707,10 @@ int launch_lrc(mg_ctx *ctx, const uint8_t *d_codes, int n, int denom, double *d_
     return MG_OK;
 }
 
-size_t feat_window_smem(int stride, int span_cap)
+size_t feat_window_smem(int stride, int span_cap, int n_pairs)
 {
-    return (size_t)kRecipN * 8 + MG_NLRC * 8 + (size_t)PF_ROWS * stride * 2 + (size_t)span_cap + 8;
+    return (size_t)kRecipN * 8 + MG_NLRC * 8 + (size_t)kWarpsPerBlock * GW_FIELDS * 32 * 4 + (size_t)(2 * n_pairs + 2) * 4 +
+           (size_t)PF_ROWS * stride * 2 + (size_t)span_cap + 8;
 }
 
 int launch_feat_setup(mg_ctx *ctx)
@@ -648,7 +723,7 @@ int launch_feat_grid(mg_ctx *ctx, const mg_panel *p, int task0, int task1, int64
                      double *d_logistic, double *d_x)
 {
     if (task1 <= task0) return MG_OK;
-    const size_t smem = feat_window_smem(p->pf_stride, p->span_cap);
+    const size_t smem = feat_window_smem(p->pf_stride, p->span_cap, (int)ctx->cfg.ext_len.size());
     if (smem > 200 * 1024) { ctx->err = "capture size too large for the K-feat window tables"; return MG_ERR_INVALID; }
     int blocks = task1 - task0;
     const int cap = ctx->sm_count * 8;

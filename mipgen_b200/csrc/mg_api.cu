@@ -159,6 +159,21 @@ extern "C" int mg_create(int device, mg_ctx **out)
 
     std::vector<uint32_t> fd = build_feature_descriptors(false), fdw = build_feature_descriptors(true);
     if (fd.size() != MG_NFEAT || fdw.size() != MG_NFEAT) { g_create_err = "internal: feature table size"; delete ctx; return MG_ERR_INVALID; }
+    // K-feat's window kernel hard-codes which kind/part each feature index has; verify it against the table
+    for (int f = 0; f < MG_NFEAT; f++) {
+        uint32_t kind, part = 0;
+        if (f < 21) { kind = FK_RATIO; part = 0; } else if (f == 21) { kind = FK_LEN; part = 0; }
+        else if (f < 66) kind = FK_LRC;
+        else if (f < 151) { kind = FK_RATIO; part = 1; } else if (f == 151) { kind = FK_LEN; part = 1; }
+        else if (f < 173) { kind = FK_RATIO; part = 2; } else if (f == 173) { kind = FK_LEN; part = 2; }
+        else if (f < 190) kind = FK_JUNC;
+        else kind = FK_COPY;
+        bool ok = (fdw[f] & 7) == kind && (kind == FK_LRC || kind == FK_JUNC || kind == FK_COPY || ((fdw[f] >> 3) & 3) == part);
+        if (kind == FK_LRC) ok = ok && ((fdw[f] >> 23) & 255) == (uint32_t)(f - 22);
+        if (kind == FK_JUNC) ok = ok && ((fdw[f] >> 23) & 255) == (uint32_t)(f - 174);
+        if (kind == FK_COPY) ok = ok && ((fdw[f] >> 23) & 255) == (uint32_t)(f - 190);
+        if (!ok) { g_create_err = "internal: feature layout does not match K-feat's specialisation"; delete ctx; return MG_ERR_INVALID; }
+    }
     if ((e = cudaMalloc(&ctx->d_fdesc, MG_NFEAT * sizeof(uint32_t))) != cudaSuccess) return fail("cudaMalloc", e);
     if ((e = cudaMalloc(&ctx->d_fdesc_win, MG_NFEAT * sizeof(uint32_t))) != cudaSuccess) return fail("cudaMalloc", e);
     cudaMemcpy(ctx->d_fdesc, fd.data(), MG_NFEAT * sizeof(uint32_t), cudaMemcpyHostToDevice);
@@ -747,12 +762,14 @@ extern "C" int mg_panel_score(mg_ctx *ctx, mg_panel *p, int want)
         if (rc == MG_OK && w_svr) rc = launch_svr(ctx, p->d_feat, p->n_cand, p->d_valid, p->d_svr);
     } else {
         // feature rows live only in a workspace: walk the panel in chunks of whole windows
+        const int64_t n_chunks = (p->n_cand + kMaxChunkRows - 1) / kMaxChunkRows;
+        const int64_t target = std::min<int64_t>(kMaxChunkRows, p->n_cand / n_chunks + (1 << 16));  // even chunks, no tiny tail
         int t0 = 0;
         while (t0 < n_tasks && rc == MG_OK) {
             const int64_t g0 = p->h_tasks[t0].g0;
             int t1 = t0 + 1;
             auto end_of = [&](int t) { return t < n_tasks ? p->h_tasks[t].g0 : p->n_cand; };
-            while (t1 < n_tasks && end_of(t1 + 1) - g0 <= kMaxChunkRows) t1++;
+            while (t1 < n_tasks && end_of(t1 + 1) - g0 <= target) t1++;
             const int64_t g1 = end_of(t1);
             if ((rc = ensure_x(ctx, g1 - g0)) != MG_OK) return rc;
             rc = launch_feat_grid(ctx, p, t0, t1, g0, g1 - g0, p->d_valid, w_log ? p->d_logistic : nullptr, ctx->d_x);
