@@ -213,6 +213,8 @@ def main():
     if args.impl == "reference":
         return reference_arm(args, rank, world, cfg, work, config)
 
+    # keep stdout for the one JSON line: NCCL's version banner / debug lines go to stderr
+    os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
     import torch
     import mipgen_b200 as mg
     if world > 1:
