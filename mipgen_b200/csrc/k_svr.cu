@@ -71,21 +71,45 @@ __device__ __forceinline__ void dmma884(double &c0, double &c1, double a, double
     asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
 }
 
+// exp(t) for t <= 0, FP64, ~1 ulp: t = (64 n + j) ln2/64 + r, |r| <= ln2/128;
+//   exp(t) = 2^n * 2^(j/64) * (1 + r + r^2/2 + r^3/6 + r^4/24 + r^5/120)      (next term 3.5e-17)
+// 10 FP64 instructions instead of ~21 for CUDA's exp(): the epilogue shares the FP64 pipe with
+// the DMMAs (profiles/fp64_peaks.json), so every instruction saved here is contraction time.
+// Results below 2^-1021 (t < -708) are flushed to 0: libsvm would add alpha * 1e-308.
+__device__ __forceinline__ double exp_nonpos(double t, const double *__restrict__ tab64)
+{
+    const double kMagic = 6755399441055744.0;  // 1.5 * 2^52: the low word of (x + kMagic) is rint(x)
+    const double kf0 = fma(t, 92.332482616893657, kMagic);
+    const int k = __double2loint(kf0);
+    const double kf = kf0 - kMagic;
+    double r = fma(kf, -0x1.62e42fee00000p-7, t);  // ln2/64 split: high part has 21 trailing zero bits
+    r = fma(kf, -0x1.a39ef35793c76p-39, r);
+    double q = fma(r, 1.0 / 120.0, 1.0 / 24.0);
+    q = fma(q, r, 1.0 / 6.0);
+    q = fma(q, r, 0.5);
+    const double p = fma(r * r, q, r);
+    const double tj = tab64[k & 63];
+    const double v = fma(tj, p, tj);
+    const double scaled = __hiloint2double(__double2hiint(v) + ((k >> 6) << 20), __double2loint(v));
+    return t < -708.0 ? 0.0 : scaled;
+}
+
 constexpr int kSlabs = MG_NFEAT / SVR_BK;                 // 6
 constexpr int kXsDoubles = SVR_BM * SVR_LDX;              // 12800
 constexpr int kBsDoubles = SVR_BN * SVR_LDB;              // 2560 per stage
-constexpr size_t kSmemBytes = (size_t)(kXsDoubles + SVR_STAGES * kBsDoubles + 2 * SVR_BM) * 8 + 16 * 8 + SVR_BM * 4;
+constexpr size_t kSmemBytes = (size_t)(kXsDoubles + SVR_STAGES * kBsDoubles + 2 * SVR_BM + 64) * 8 + 16 * 8 + SVR_BM * 4;
 
 __global__ void __launch_bounds__(SVR_THREADS, 1)
 k_svr_dmma(const double *__restrict__ x, int64_t n, const double *__restrict__ sv_tiled, const double *__restrict__ ss,
-           const double *__restrict__ alpha, int n_sv_pad, double gamma, double rho, const uint8_t *__restrict__ valid,
-           double *__restrict__ out)
+           const double *__restrict__ alpha, const double *__restrict__ exp2_tab, int n_sv_pad, double gamma, double rho,
+           const uint8_t *__restrict__ valid, double *__restrict__ out)
 {
     extern __shared__ __align__(128) uint8_t smem_raw[];
     double *Xs = reinterpret_cast<double *>(smem_raw);
     double *Bs = Xs + kXsDoubles;
     double *red = Bs + SVR_STAGES * kBsDoubles;  // [2][64]
-    uint64_t *bars = reinterpret_cast<uint64_t *>(red + 2 * SVR_BM);
+    double *etab = red + 2 * SVR_BM;             // [64] 2^(j/64)
+    uint64_t *bars = reinterpret_cast<uint64_t *>(etab + 64);
     uint64_t *full = bars, *empty = bars + SVR_STAGES, *xfull = bars + 2 * SVR_STAGES;
     int *rowflag = reinterpret_cast<int *>(bars + 16);  // [64] non-finite feature row
 
@@ -93,6 +117,7 @@ k_svr_dmma(const double *__restrict__ x, int64_t n, const double *__restrict__ s
     const int64_t row0 = (int64_t)blockIdx.x * SVR_BM;
     const int n_chunks = n_sv_pad / SVR_BN;
 
+    if (threadIdx.x >= 64 && threadIdx.x < 128) etab[threadIdx.x - 64] = exp2_tab[threadIdx.x - 64];
     if (threadIdx.x == 0) {
         for (int s = 0; s < SVR_STAGES; s++) { mbar_init(&full[s], 1); mbar_init(&empty[s], SVR_CONSUMER_WARPS); }
         mbar_init(xfull, 1);
@@ -197,8 +222,8 @@ k_svr_dmma(const double *__restrict__ x, int64_t n, const double *__restrict__ s
                     double d1 = fma(-2.0, acc[mi][ni][1], xx[mi] + ssv[ni].y);
                     d0 = fmax(d0, 0.0);
                     d1 = fmax(d1, 0.0);
-                    part[mi] = fma(alv[ni].x, exp(ngamma * d0), part[mi]);
-                    part[mi] = fma(alv[ni].y, exp(ngamma * d1), part[mi]);
+                    part[mi] = fma(alv[ni].x, exp_nonpos(ngamma * d0, etab), part[mi]);
+                    part[mi] = fma(alv[ni].y, exp_nonpos(ngamma * d1, etab), part[mi]);
                 }
         }
 
@@ -268,7 +293,7 @@ int launch_svr(mg_ctx *ctx, const double *d_x, int64_t n, const uint8_t *d_valid
     if (n <= 0) return MG_OK;
     const int64_t tiles = (n + SVR_BM - 1) / SVR_BM;
     mg_time_begin(ctx, TM_SVR, n);
-    k_svr_dmma<<<(unsigned)tiles, SVR_THREADS, kSmemBytes, ctx->stream>>>(d_x, n, ctx->d_sv_tiled, ctx->d_ss, ctx->d_alpha, ctx->n_sv_pad,
+    k_svr_dmma<<<(unsigned)tiles, SVR_THREADS, kSmemBytes, ctx->stream>>>(d_x, n, ctx->d_sv_tiled, ctx->d_ss, ctx->d_alpha, ctx->d_exp2tab, ctx->n_sv_pad,
                                                                        ctx->gamma, ctx->rho, d_valid, d_out);
     mg_time_end(ctx);
     CUDA_TRY(ctx, cudaGetLastError());

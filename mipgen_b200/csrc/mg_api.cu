@@ -184,6 +184,10 @@ extern "C" int mg_create(int device, mg_ctx **out)
     logtab[101] = 2.0;
     if ((e = cudaMalloc(&ctx->d_logcopy, sizeof logtab)) != cudaSuccess) return fail("cudaMalloc", e);
     cudaMemcpy(ctx->d_logcopy, logtab, sizeof logtab, cudaMemcpyHostToDevice);
+    double e2tab[64];
+    for (int j = 0; j < 64; j++) e2tab[j] = exp2((double)j / 64.0);
+    if ((e = cudaMalloc(&ctx->d_exp2tab, sizeof e2tab)) != cudaSuccess) return fail("cudaMalloc", e);
+    cudaMemcpy(ctx->d_exp2tab, e2tab, sizeof e2tab, cudaMemcpyHostToDevice);
     if ((e = cudaMalloc(&ctx->d_cfg, sizeof(DevConfig))) != cudaSuccess) return fail("cudaMalloc", e);
     uint8_t lk[MG_NLRC], lc[MG_NLRC];
     for (int i = 0; i < MG_NLRC; i++) {
@@ -217,7 +221,7 @@ extern "C" void mg_destroy(mg_ctx *ctx)
     for (auto e : ctx->ev_free) cudaEventDestroy(e);
     if (ctx->sw_a) { cudaEventDestroy(ctx->sw_a); cudaEventDestroy(ctx->sw_b); }
     free_model(ctx);
-    cudaFree(ctx->d_x); cudaFree(ctx->d_fdesc); cudaFree(ctx->d_fdesc_win); cudaFree(ctx->d_logcopy); cudaFree(ctx->d_cfg);
+    cudaFree(ctx->d_x); cudaFree(ctx->d_fdesc); cudaFree(ctx->d_fdesc_win); cudaFree(ctx->d_logcopy); cudaFree(ctx->d_exp2tab); cudaFree(ctx->d_cfg);
     cudaStreamDestroy(ctx->stream);
     delete ctx;
 }

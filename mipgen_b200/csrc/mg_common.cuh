@@ -125,6 +125,7 @@ struct mg_ctx {
     uint32_t *d_fdesc = nullptr;    // [192] packed feature descriptors (explicit front-end: count slots)
     uint32_t *d_fdesc_win = nullptr;  // [192] the same with prefix-table rows (window front-end)
     double *d_logcopy = nullptr;    // [102] log10(copy) for copy 0..100 (glibc), [101] = 2.0
+    double *d_exp2tab = nullptr;    // [64] 2^(j/64), K-svr's exp table
     // model
     bool has_model = false;
     int n_sv = 0, n_sv_pad = 0;
