@@ -122,6 +122,12 @@ int mg_load_svr_model(mg_ctx *ctx, const char *path);
 int mg_set_svr_model(mg_ctx *ctx, const double *sv, const double *alpha, int n_sv, int n_feat,
                      double gamma, double rho);
 int mg_model_info(const mg_ctx *ctx, int *n_sv, double *gamma, double *rho);
+/* How region grids are SVR-scored: 0 = automatic (the factored kernel when the arm-pair table
+ * fits its shared-memory tables, else the dense contraction), 1 = dense DMMA contraction,
+ * 2 = factored (error if it does not fit).  Both compute the same FP64 decision value. */
+int mg_set_svr_mode(mg_ctx *ctx, int mode);
+/* > 0 (the factored kernel's window size) if the current config fits the factored kernel */
+int mg_svr_factored_available(const mg_ctx *ctx);
 /* svm_predict for n dense rows x[i*ld .. i*ld+191] (features 1..192). out[n]. */
 int mg_svr_predict(mg_ctx *ctx, const double *x, long n, long ld, double *out);
 /* Same arithmetic order as libsvm (direct (x-s)^2 form, sequential sums), one thread

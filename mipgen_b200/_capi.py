@@ -62,6 +62,8 @@ SYMBOLS = [
     ("mg_get_timings", C.c_int, [C.c_void_p, C.POINTER(MgTimings)]),
     ("mg_load_svr_model", C.c_int, [C.c_void_p, C.c_char_p]),
     ("mg_set_svr_model", C.c_int, [C.c_void_p, c_double_p, c_double_p, C.c_int, C.c_int, C.c_double, C.c_double]),
+    ("mg_set_svr_mode", C.c_int, [C.c_void_p, C.c_int]),
+    ("mg_svr_factored_available", C.c_int, [C.c_void_p]),
     ("mg_model_info", C.c_int, [C.c_void_p, c_int_p, c_double_p, c_double_p]),
     ("mg_svr_predict", C.c_int, [C.c_void_p, c_double_p, C.c_long, C.c_long, c_double_p]),
     ("mg_svr_predict_direct", C.c_int, [C.c_void_p, c_double_p, C.c_long, C.c_long, c_double_p]),
@@ -241,6 +243,13 @@ class Context:
         alpha = np.ascontiguousarray(alpha, np.float64)
         self._check(self.lib.mg_set_svr_model(self.h, _ptr(sv, c_double_p), _ptr(alpha, c_double_p), sv.shape[0],
                                               sv.shape[1], gamma, rho))
+
+    def set_svr_mode(self, mode: int) -> None:
+        """0 auto, 1 dense DMMA contraction, 2 factored."""
+        self._check(self.lib.mg_set_svr_mode(self.h, mode))
+
+    def svr_factored_available(self) -> int:
+        return int(self.lib.mg_svr_factored_available(self.h))
 
     def model_info(self):
         n, g, r = C.c_int(), C.c_double(), C.c_double()

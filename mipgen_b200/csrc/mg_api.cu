@@ -189,6 +189,7 @@ extern "C" int mg_create(int device, mg_ctx **out)
     if ((e = cudaMalloc(&ctx->d_exp2tab, sizeof e2tab)) != cudaSuccess) return fail("cudaMalloc", e);
     cudaMemcpy(ctx->d_exp2tab, e2tab, sizeof e2tab, cudaMemcpyHostToDevice);
     if ((e = cudaMalloc(&ctx->d_cfg, sizeof(DevConfig))) != cudaSuccess) return fail("cudaMalloc", e);
+    if ((e = cudaMalloc(&ctx->d_fact, sizeof(DevFact))) != cudaSuccess) return fail("cudaMalloc", e);
     uint8_t lk[MG_NLRC], lc[MG_NLRC];
     for (int i = 0; i < MG_NLRC; i++) {
         int k = (int)strlen(kFeatureMers[i]), code = 0;
@@ -196,7 +197,8 @@ extern "C" int mg_create(int device, mg_ctx **out)
         lk[i] = (uint8_t)k;
         lc[i] = (uint8_t)code;
     }
-    if (mg_upload_lrc_tables(ctx, lk, lc) != MG_OK || launch_svr_setup(ctx) != MG_OK || launch_feat_setup(ctx) != MG_OK) {
+    if (mg_upload_lrc_tables(ctx, lk, lc) != MG_OK || launch_svr_setup(ctx) != MG_OK || launch_feat_setup(ctx) != MG_OK ||
+        launch_fact_setup(ctx) != MG_OK) {
         g_create_err = ctx->err;
         delete ctx;
         return MG_ERR_CUDA;
@@ -207,6 +209,8 @@ extern "C" int mg_create(int device, mg_ctx **out)
 
 static void free_model(mg_ctx *ctx)
 {
+    cudaFree(ctx->d_fact_blob);
+    ctx->d_fact_blob = nullptr;
     cudaFree(ctx->d_sv); cudaFree(ctx->d_sv_tiled); cudaFree(ctx->d_ss); cudaFree(ctx->d_alpha); cudaFree(ctx->d_tail);
     ctx->d_sv = ctx->d_sv_tiled = ctx->d_ss = ctx->d_alpha = ctx->d_tail = nullptr;
     ctx->has_model = false;
@@ -221,7 +225,7 @@ extern "C" void mg_destroy(mg_ctx *ctx)
     for (auto e : ctx->ev_free) cudaEventDestroy(e);
     if (ctx->sw_a) { cudaEventDestroy(ctx->sw_a); cudaEventDestroy(ctx->sw_b); }
     free_model(ctx);
-    cudaFree(ctx->d_x); cudaFree(ctx->d_fdesc); cudaFree(ctx->d_fdesc_win); cudaFree(ctx->d_logcopy); cudaFree(ctx->d_exp2tab); cudaFree(ctx->d_cfg);
+    cudaFree(ctx->d_x); cudaFree(ctx->d_fdesc); cudaFree(ctx->d_fdesc_win); cudaFree(ctx->d_logcopy); cudaFree(ctx->d_exp2tab); cudaFree(ctx->d_cfg); cudaFree(ctx->d_fact);
     cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
@@ -329,12 +333,57 @@ extern "C" int mg_set_config(mg_ctx *ctx, const mg_config *c)
     if (e != cudaSuccess) { ctx->err = std::string("config upload: ") + cudaGetErrorString(e); return MG_ERR_CUDA; }
     ctx->cfg = h;
     ctx->has_cfg = true;
+
+    // factored SVR: distinct arm lengths / arm sums, and the largest window whose tables fit in shared memory
+    ctx->fact_ok = false;
+    {
+        DevFact *f = new DevFact();
+        memset(f, 0, sizeof *f);
+        std::vector<int> exts, ligs, sums;
+        bool ok = h.max_sum - h.min_sum < FACT_MAX_SPAN;
+        for (int i = 0; i < c->n_pairs && ok; i++) {
+            if (h.ext_len[i] >= FACT_MAX_LEN || h.lig_len[i] >= FACT_MAX_LEN) ok = false;
+            exts.push_back(h.ext_len[i]); ligs.push_back(h.lig_len[i]); sums.push_back(h.ext_len[i] + h.lig_len[i]);
+        }
+        auto uniq = [](std::vector<int> &v) { std::sort(v.begin(), v.end()); v.erase(std::unique(v.begin(), v.end()), v.end()); };
+        uniq(exts); uniq(ligs); uniq(sums);
+        if (ok) {
+            for (int i = 0; i < FACT_MAX_LEN; i++) f->ext_idx[i] = f->lig_idx[i] = -1;
+            for (int i = 0; i < FACT_MAX_SPAN; i++) f->sum_idx[i] = -1;
+            for (size_t i = 0; i < exts.size(); i++) f->ext_idx[exts[i]] = (int)i;
+            for (size_t i = 0; i < ligs.size(); i++) f->lig_idx[ligs[i]] = (int)i;
+            for (size_t i = 0; i < sums.size(); i++) f->sum_idx[sums[i] - h.min_sum] = (int)i;
+            for (int i = 0; i < c->n_pairs; i++) { f->pair_e[i] = h.ext_len[i]; f->pair_l[i] = h.lig_len[i]; }
+            f->n_pairs = c->n_pairs; f->n_cap = h.n_cap; f->n_ext = (int)exts.size(); f->n_lig = (int)ligs.size();
+            f->n_sums = (int)sums.size(); f->min_sum = h.min_sum; f->max_sum = h.max_sum;
+            const int dsum = h.max_sum - h.min_sum;
+            auto pad8 = [](int v) { return (v + 7) & ~7; };
+            for (int W = 8; W >= 1 && !ctx->fact_ok; W /= 2) {
+                if (W * c->n_pairs > FACT_THREADS) continue;
+                const int RA0 = pad8(W * f->n_ext), RA1 = pad8(W * f->n_lig);
+                const int RQ0 = pad8((W + dsum) * f->n_lig), RQ1 = pad8((W + dsum) * f->n_ext), RI = pad8(W * f->n_sums);
+                f->cap_FA = std::max(RA0 * FACT_LD_EXT, RA1 * FACT_LD_LIG);
+                f->cap_FQ = std::max(RQ0 * FACT_LD_LIG, RQ1 * FACT_LD_EXT);
+                f->cap_FI = RI * FACT_LD_INS;
+                f->cap_R = std::max(RA0 + RQ0, RA1 + RQ1) + RI;
+                size_t doubles = (size_t)f->cap_FA + f->cap_FQ + f->cap_FI + f->cap_R + (size_t)f->cap_R * (FACT_C + 1) + 2 * FACT_BLOB +
+                                 2 * FACT_C + 64;
+                size_t bytes = doubles * 8 + 16 + (size_t)f->cap_R * 4 + 64;
+                if (bytes <= FACT_SMEM_LIMIT) { f->W = W; ctx->fact_ok = true; ctx->fact_W = W; ctx->fact_smem = bytes; }
+            }
+        }
+        if (ctx->fact_ok) e = cudaMemcpy(ctx->d_fact, f, sizeof *f, cudaMemcpyHostToDevice);
+        delete f;
+        if (e != cudaSuccess) { ctx->err = std::string("factored config upload: ") + cudaGetErrorString(e); return MG_ERR_CUDA; }
+    }
     return MG_OK;
 }
 
 // ---------------------------------------------------------------------------
 // model
 // ---------------------------------------------------------------------------
+static int ensure_x(mg_ctx *ctx, int64_t rows);
+
 static int upload_model(mg_ctx *ctx, const std::vector<double> &dense, const std::vector<double> &tail, const std::vector<double> &alpha,
                         int n_sv, double gamma, double rho)
 {
@@ -370,8 +419,44 @@ static int upload_model(mg_ctx *ctx, const std::vector<double> &dense, const std
     CUDA_TRY(ctx, cudaMemcpy(ctx->d_sv, sv.data(), sv.size() * 8, cudaMemcpyHostToDevice));
     CUDA_TRY(ctx, cudaMemcpy(ctx->d_ss, ss.data(), ss.size() * 8, cudaMemcpyHostToDevice));
     CUDA_TRY(ctx, cudaMemcpy(ctx->d_alpha, al.data(), al.size() * 8, cudaMemcpyHostToDevice));
+    // factored kernel: per chunk of FACT_C support vectors, the ext / lig / insert blocks in the padded
+    // shared-memory layout, followed by the blocks' squared norms (one bulk copy per chunk)
+    {
+        const int n_chunks = pad / FACT_C;
+        std::vector<double> blob((size_t)n_chunks * FACT_BLOB, 0.0);
+        for (int i = 0; i < pad; i++) {
+            double *b = &blob[(size_t)(i / FACT_C) * FACT_BLOB];
+            const int r = i % FACT_C;
+            const double *srow = &sv[(size_t)i * MG_NFEAT];
+            double se = 0, sl = 0, si = 0;
+            for (int k = 0; k < 22; k++) { b[FACT_OFF_EXT + r * FACT_LD_EXT + k] = srow[k]; se += srow[k] * srow[k]; }
+            b[FACT_OFF_EXT + r * FACT_LD_EXT + 22] = srow[190]; se += srow[190] * srow[190];
+            for (int k = 0; k < 38; k++) { b[FACT_OFF_LIG + r * FACT_LD_LIG + k] = srow[152 + k]; sl += srow[152 + k] * srow[152 + k]; }
+            b[FACT_OFF_LIG + r * FACT_LD_LIG + 38] = srow[191]; sl += srow[191] * srow[191];
+            for (int k = 0; k < 86; k++) { b[FACT_OFF_INS + r * FACT_LD_INS + k] = srow[66 + k]; si += srow[66 + k] * srow[66 + k]; }
+            b[FACT_OFF_SS + r] = se; b[FACT_OFF_SS + FACT_C + r] = sl; b[FACT_OFF_SS + 2 * FACT_C + r] = si;
+        }
+        CUDA_TRY(ctx, cudaMalloc(&ctx->d_fact_blob, blob.size() * 8));
+        CUDA_TRY(ctx, cudaMemcpy(ctx->d_fact_blob, blob.data(), blob.size() * 8, cudaMemcpyHostToDevice));
+    }
     ctx->n_sv = n_sv; ctx->n_sv_pad = pad; ctx->gamma = gamma; ctx->rho = rho;
     ctx->has_model = true;
+    // SVR value of the all-zero vector (what an invalid candidate scores, SVMipv4.cpp:63-68), from the dense kernel
+    {
+        int rc = ensure_x(ctx, SVR_BM);
+        if (rc != MG_OK) return rc;
+        double *d_z = nullptr;
+        CUDA_TRY(ctx, cudaMalloc(&d_z, SVR_BM * 8));
+        CUDA_TRY(ctx, cudaMemsetAsync(ctx->d_x, 0, (size_t)SVR_BM * MG_NFEAT * 8, ctx->stream));
+        rc = launch_svr(ctx, ctx->d_x, SVR_BM, nullptr, d_z);
+        if (rc == MG_OK) {
+            cudaError_t e2 = cudaMemcpyAsync(&ctx->zero_score, d_z, 8, cudaMemcpyDeviceToHost, ctx->stream);
+            if (e2 == cudaSuccess) e2 = cudaStreamSynchronize(ctx->stream);
+            if (e2 != cudaSuccess) { ctx->err = cudaGetErrorString(e2); rc = MG_ERR_CUDA; }
+        }
+        cudaFree(d_z);
+        if (rc != MG_OK) return rc;
+    }
     return MG_OK;
 }
 
@@ -438,6 +523,15 @@ extern "C" int mg_load_svr_model(mg_ctx *ctx, const char *path)
     alpha.resize(total_sv);
     return upload_model(ctx, dense, tail, alpha, total_sv, gamma, rho);
 }
+
+extern "C" int mg_set_svr_mode(mg_ctx *ctx, int mode)
+{
+    if (!ctx || mode < 0 || mode > 2) return MG_ERR_INVALID;
+    ctx->svr_mode = mode;
+    return MG_OK;
+}
+
+extern "C" int mg_svr_factored_available(const mg_ctx *ctx) { return ctx && ctx->fact_ok ? ctx->fact_W : 0; }
 
 extern "C" int mg_model_info(const mg_ctx *ctx, int *n_sv, double *gamma, double *rho)
 {
@@ -635,6 +729,7 @@ extern "C" void mg_panel_destroy(mg_panel *p)
     if (!p) return;
     cudaSetDevice(p->ctx->device);
     cudaStreamSynchronize(p->ctx->stream);
+    cudaFree(p->d_ftasks); cudaFree(p->d_w);
     cudaFree(p->d_regions); cudaFree(p->d_tasks); cudaFree(p->d_codes); cudaFree(p->d_lrc); cudaFree(p->d_copies);
     cudaFree(p->d_valid); cudaFree(p->d_logistic); cudaFree(p->d_svr); cudaFree(p->d_feat);
     delete p;
@@ -685,6 +780,7 @@ extern "C" int mg_panel_create(mg_ctx *ctx, const mg_region *regions, int n, mg_
         int64_t total_scan = 0;
         for (int i = 0; i < n; i++) total_scan += p->h_regions[i].n_scan;
         int W = (int)std::min<int64_t>(64, std::max<int64_t>(8, total_scan / ((int64_t)ctx->sm_count * 6)));
+        W = W / 8 * 8;  // factored-SVR windows (8, 4, 2 or 1 scan starts) must nest inside K-feat windows
         const int64_t per_scan = (int64_t)ctx->cfg.n_cap * (int64_t)ctx->cfg.ext_len.size() * 2;
         while (W > 1 && W * per_scan > (1 << 24)) W /= 2;  // keep a window's candidate count in int range
         for (int i = 0; i < n; i++)
@@ -694,6 +790,24 @@ extern "C" int mg_panel_create(mg_ctx *ctx, const mg_region *regions, int n, mg_
                 t.g0 = p->h_regions[i].grid_off + (int64_t)si * per_scan;
                 p->h_tasks.push_back(t);
             }
+        // factored-SVR tasks, grouped by K-feat window so a chunk of windows is a contiguous task range
+        p->ftask_start.assign(p->h_tasks.size() + 1, 0);
+        if (ctx->fact_ok && W % ctx->fact_W == 0) {
+            for (size_t k = 0; k < p->h_tasks.size(); k++) {
+                const DevTask &t = p->h_tasks[k];
+                p->ftask_start[k] = (int)p->h_ftasks.size();
+                for (int si = 0; si < t.nsi; si += ctx->fact_W)
+                    for (int ci = 0; ci < ctx->cfg.n_cap; ci++)
+                        for (int strand = 0; strand < 2; strand++) {
+                            DevFTask f;
+                            f.g0 = p->h_regions[t.region].grid_off;
+                            f.region = t.region; f.si0 = t.si0 + si; f.nsi = std::min(ctx->fact_W, t.nsi - si);
+                            f.ci = ci; f.strand = strand; f.pad = 0;
+                            p->h_ftasks.push_back(f);
+                        }
+            }
+            p->ftask_start[p->h_tasks.size()] = (int)p->h_ftasks.size();
+        }
         p->span_cap = W + ctx->cfg.max_arm + ctx->cfg.max_capture - ctx->cfg.min_arm + 4;
         int words = (p->span_cap + 2) / 2;
         if (words % 2 == 0) words++;  // odd word stride: table rows spread over the banks
@@ -716,6 +830,10 @@ extern "C" int mg_panel_create(mg_ctx *ctx, const mg_region *regions, int n, mg_
         P_TRY(cudaMalloc(&p->d_regions, (size_t)n * sizeof(DevRegion)));
         P_TRY(cudaMemcpyAsync(d_ascii, ascii.data(), (size_t)codes, cudaMemcpyHostToDevice, ctx->stream));
         P_TRY(cudaMemcpyAsync(p->d_regions, p->h_regions.data(), (size_t)n * sizeof(DevRegion), cudaMemcpyHostToDevice, ctx->stream));
+        if (!p->h_ftasks.empty()) {
+            P_TRY(cudaMalloc(&p->d_ftasks, p->h_ftasks.size() * sizeof(DevFTask)));
+            P_TRY(cudaMemcpyAsync(p->d_ftasks, p->h_ftasks.data(), p->h_ftasks.size() * sizeof(DevFTask), cudaMemcpyHostToDevice, ctx->stream));
+        }
         if (!p->h_tasks.empty()) {
             P_TRY(cudaMalloc(&p->d_tasks, p->h_tasks.size() * sizeof(DevTask)));
             P_TRY(cudaMemcpyAsync(p->d_tasks, p->h_tasks.data(), p->h_tasks.size() * sizeof(DevTask), cudaMemcpyHostToDevice, ctx->stream));
@@ -759,11 +877,30 @@ extern "C" int mg_panel_score(mg_ctx *ctx, mg_panel *p, int want)
     }
     int rc = MG_OK;
     const int n_tasks = (int)p->h_tasks.size();
+    // factored SVR when the configuration fits its tables (mode 0/2); dense otherwise (mode 1, or as fallback)
+    const bool fact = w_svr && ctx->svr_mode != 1 && ctx->fact_ok && !p->h_ftasks.empty();
+    if (w_svr && ctx->svr_mode == 2 && !fact) {
+        ctx->err = "factored SVR requested but the configuration does not fit its shared-memory tables";
+        return MG_ERR_INVALID;
+    }
+    if (fact) {
+        if (!p->d_w || p->w_n_sv_pad != ctx->n_sv_pad) {
+            cudaFree(p->d_w);
+            p->d_w = nullptr;
+            CUDA_TRY(ctx, cudaMalloc(&p->d_w, (size_t)p->n_regions * ctx->n_sv_pad * 8));
+            p->w_n_sv_pad = ctx->n_sv_pad;
+        }
+        if ((rc = launch_lrc_weights(ctx, p, p->d_w)) != MG_OK) return rc;
+    }
+    auto svr_range = [&](int t0, int t1, const double *xbuf, int64_t g0, int64_t g1) {
+        if (fact) return launch_svr_fact(ctx, p, p->ftask_start[t0], p->ftask_start[t1], xbuf, g0, g1 - g0, p->d_valid, p->d_w, p->d_svr);
+        return launch_svr(ctx, xbuf, g1 - g0, p->d_valid + g0, p->d_svr + g0);
+    };
     if (!w_svr && !w_feat) {
         rc = launch_feat_grid(ctx, p, 0, n_tasks, 0, p->n_cand, p->d_valid, w_log ? p->d_logistic : nullptr, nullptr);
     } else if (w_feat) {
         rc = launch_feat_grid(ctx, p, 0, n_tasks, 0, p->n_cand, p->d_valid, w_log ? p->d_logistic : nullptr, p->d_feat);
-        if (rc == MG_OK && w_svr) rc = launch_svr(ctx, p->d_feat, p->n_cand, p->d_valid, p->d_svr);
+        if (rc == MG_OK && w_svr) rc = svr_range(0, n_tasks, p->d_feat, 0, p->n_cand);
     } else {
         // feature rows live only in a workspace: walk the panel in chunks of whole windows
         const int64_t n_chunks = (p->n_cand + kMaxChunkRows - 1) / kMaxChunkRows;
@@ -777,7 +914,7 @@ extern "C" int mg_panel_score(mg_ctx *ctx, mg_panel *p, int want)
             const int64_t g1 = end_of(t1);
             if ((rc = ensure_x(ctx, g1 - g0)) != MG_OK) return rc;
             rc = launch_feat_grid(ctx, p, t0, t1, g0, g1 - g0, p->d_valid, w_log ? p->d_logistic : nullptr, ctx->d_x);
-            if (rc == MG_OK) rc = launch_svr(ctx, ctx->d_x, g1 - g0, p->d_valid + g0, p->d_svr + g0);
+            if (rc == MG_OK) rc = svr_range(t0, t1, ctx->d_x, g0, g1);
             t0 = t1;
         }
     }

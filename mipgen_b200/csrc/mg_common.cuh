@@ -103,6 +103,39 @@ __host__ __device__ inline uint32_t fd_pack(uint32_t kind, uint32_t part, uint32
 #define SVR_THREADS ((SVR_CONSUMER_WARPS + 1) * 32)
 
 // ---------------------------------------------------------------------------
+// factored SVR (k_svr_fact.cu): block sizes, padded strides, per-chunk blob layout
+// ---------------------------------------------------------------------------
+#define FACT_C 16          // support vectors per chunk
+#define FACT_THREADS 512
+#define FACT_K_EXT 24      // 22 ext features + log copy, padded to a multiple of 4
+#define FACT_K_LIG 40      // 38 lig features + log copy
+#define FACT_K_INS 88      // 86 insert features
+#define FACT_LD_EXT 28     // strides == 12 mod 16 doubles: conflict-free LDS.64 fragment loads
+#define FACT_LD_LIG 44
+#define FACT_LD_INS 92
+#define FACT_OFF_EXT 0
+#define FACT_OFF_LIG (FACT_C * FACT_LD_EXT)
+#define FACT_OFF_INS (FACT_OFF_LIG + FACT_C * FACT_LD_LIG)
+#define FACT_OFF_SS (FACT_OFF_INS + FACT_C * FACT_LD_INS)   // ss_ext[C], ss_lig[C], ss_ins[C]
+#define FACT_BLOB (FACT_OFF_SS + 3 * FACT_C)                // doubles per chunk
+#define FACT_SMEM_LIMIT (227 * 1024)
+#define FACT_MAX_LEN 64
+#define FACT_MAX_SPAN 128
+
+struct DevFact {
+    int n_pairs, n_cap, n_ext, n_lig, n_sums, min_sum, max_sum, W;
+    int cap_FA, cap_FQ, cap_FI, cap_R;   // shared-memory capacities in doubles / rows
+    int ext_idx[FACT_MAX_LEN], lig_idx[FACT_MAX_LEN], sum_idx[FACT_MAX_SPAN];
+    int pair_e[MG_MAX_PAIRS], pair_l[MG_MAX_PAIRS];
+};
+
+// one factored-SVR work item: W scan starts of one region, one capture size, one strand
+struct DevFTask {
+    int64_t g0;   // grid offset of the region
+    int region, si0, nsi, ci, strand, pad;
+};
+
+// ---------------------------------------------------------------------------
 // host context
 // ---------------------------------------------------------------------------
 struct HostConfig {
@@ -135,6 +168,14 @@ struct mg_ctx {
     double *d_ss = nullptr;     // [n_sv_pad] ||s||^2 (incl. features beyond 192)
     double *d_alpha = nullptr;  // [n_sv_pad], 0 in the padding
     double *d_tail = nullptr;   // [n_sv_pad] sum of squares of SV features with index > 192
+    // factored SVR
+    int svr_mode = 0;           // 0 auto (factored when the config fits), 1 dense, 2 factored
+    bool fact_ok = false;       // config fits the factored kernel's shared-memory tables
+    int fact_W = 0;
+    size_t fact_smem = 0;
+    DevFact *d_fact = nullptr;
+    double *d_fact_blob = nullptr;  // [n_sv_pad/FACT_C][FACT_BLOB] per-chunk SV blocks + block norms
+    double zero_score = 0;          // SVR value of the all-zero vector (invalid candidates)
     // workspace
     double *d_x = nullptr;      // feature rows of the chunk in flight
     size_t x_rows_cap = 0;
@@ -156,6 +197,11 @@ struct mg_panel {
     DevRegion *d_regions = nullptr;
     std::vector<DevTask> h_tasks;  // K-feat windows, ascending in g0
     DevTask *d_tasks = nullptr;
+    std::vector<DevFTask> h_ftasks;     // factored-SVR tasks, grouped by K-feat window
+    std::vector<int> ftask_start;       // [n_tasks+1] first factored task of each K-feat window
+    DevFTask *d_ftasks = nullptr;
+    double *d_w = nullptr;              // [n_regions][n_sv_pad] alpha * exp(-g d_lrc)
+    int w_n_sv_pad = 0;
     int span_cap = 0, pf_stride = 0;
     uint8_t *d_codes = nullptr;
     int64_t n_codes = 0;
@@ -196,5 +242,9 @@ int launch_feat_explicit(mg_ctx *ctx, const DevCand *d_cands, const uint8_t *d_c
 // d_valid (nullable): rows with valid[g]==0 are written as NaN.
 int launch_svr(mg_ctx *ctx, const double *d_x, int64_t n, const uint8_t *d_valid, double *d_out);
 int launch_svr_setup(mg_ctx *ctx);
+int launch_fact_setup(mg_ctx *ctx);
+int launch_lrc_weights(mg_ctx *ctx, const mg_panel *p, double *d_w);
+int launch_svr_fact(mg_ctx *ctx, const mg_panel *p, int ftask0, int ftask1, const double *d_x, int64_t g_base, int64_t n_cand,
+                    const uint8_t *d_valid, const double *d_w, double *d_out);
 int mg_upload_lrc_tables(mg_ctx *ctx, const uint8_t *k, const uint8_t *code);
 int launch_svr_direct(mg_ctx *ctx, const double *d_x, int64_t n, int64_t ld, double *d_out);

@@ -85,7 +85,8 @@ def test_grid_equals_explicit_and_oracle_on_sample(setup):
     lrc = np.array(lrc)
     lo, sv, ft = ctx.score_candidates(cands, lrc, mg.MG_WANT_LOGISTIC | mg.MG_WANT_SVR | mg.MG_WANT_FEATURES)
     assert np.array_equal(lo, setup["lo"][picks]), "grid and explicit front-ends must agree bit for bit"
-    assert np.array_equal(sv, setup["sv"][picks])
+    # the panel was scored by the factored kernel, the explicit candidates by the dense contraction
+    assert rel_err(setup["sv"][picks], sv) <= 1e-11
     # oracle on the same sample
     h = oracle.svm_load_model(setup["model"])
     want_ft = np.array([oracle.get_parameters(c["ext"], c["lig"], c["tgt"], lrc[i]) for i, c in enumerate(cands)])
@@ -99,6 +100,7 @@ def test_grid_equals_explicit_and_oracle_on_sample(setup):
     direct = ctx.svr_predict(ft, direct=True)
     assert rel_err(direct, want_sv) <= 1e-13
     assert rel_err(sv, direct) <= 1e-9
+    assert rel_err(setup["sv"][picks], want_sv) <= 1e-9
 
 
 def test_runs_are_bitwise_reproducible(setup):

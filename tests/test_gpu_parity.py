@@ -145,6 +145,41 @@ def test_region_grid_matches_oracle(ctx, oracle):
     assert not valid.all() and valid.any()
 
 
+def test_factored_svr_matches_dense_and_oracle(ctx, oracle):
+    """The factored kernel (distinct arms/inserts, product of block factors) and the dense DMMA
+    contraction are two evaluations of the same FP64 decision function."""
+    rng = np.random.default_rng(17)
+    for cfg in (small_config((40, 43, 45), 162, 152, 5), panel.Config()):
+        genome, regions = synthetic_regions(oracle, cfg, 3, 30, 80, 77)
+        edge = panel.cut_region(genome, 150, 190, cfg, 0, "edge")   # clamped at the chromosome start
+        edge.lrc = rng.uniform(0, 0.3, 44)
+        regions.append(edge)
+        regions[1].seq = mutate(regions[1].seq, rng, 12)            # N / IUPAC / '-' : zero rows, odd run counts
+        regions[0].copies = rng.choice([0, 1, 1, 1, 2, 5, 100, 101], size=(len(cfg.oligo_sizes), len(regions[0].seq))).astype(np.int32)
+        d = tmpdir()
+        model = random_model(oracle, cfg, 150, 9, os.path.join(d, "m.model"), sparse_tail=True)
+        ctx.set_config(cfg)
+        ctx.load_svr_model(model)
+        assert ctx.svr_factored_available() > 0
+        ctx.set_svr_mode(1)
+        _o, v1, _l, dense, _f = ctx.score_regions(regions, mg.MG_WANT_SVR)
+        ctx.set_svr_mode(2)
+        _o, v2, _l, fact, _f = ctx.score_regions(regions, mg.MG_WANT_SVR)
+        _o, v3, _l, fact_f, _f = ctx.score_regions(regions, mg.MG_WANT_SVR | mg.MG_WANT_FEATURES)
+        ctx.set_svr_mode(0)
+        assert np.array_equal(v1, v2) and np.array_equal(v1, v3)
+        assert rel_err(fact, dense) <= 1e-11
+        assert np.array_equal(fact, fact_f, equal_nan=True)
+        h = oracle.svm_load_model(model)
+        a = 0
+        for r in regions[:2] + regions[3:]:
+            pass
+        want = np.concatenate([oracle.grid_region(r, cfg, h, want_logistic=False, want_svr=True)[2] for r in regions])
+        oracle.svm_free(h)
+        assert rel_err(fact, want) <= SVR_RTOL
+        assert (dense[v1.astype(bool)] == dense[v1.astype(bool)]).all()
+
+
 def test_region_grid_chunked_svr_equals_feature_path(ctx, oracle):
     """SVR through the chunked workspace path == SVR computed while features are kept."""
     cfg = small_config((40, 45))
