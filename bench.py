@@ -301,11 +301,33 @@ def main():
     clocks = sampler.stop() if rank == 0 else None
     checksum = float(np.nansum(svr_h.numpy()))
 
+    # ---- the dense DMMA contraction on the same panel (the north star's formulation), for reference ----
+    dense = None
+    if ctx.svr_factored_available():
+        ctx.set_svr_mode(1)
+        for _ in range(2):
+            pnl.score(mg.MG_WANT_SVR)
+        barrier()
+        ctx.reset_timings()
+        ctx.timer_start()
+        for _ in range(3):
+            pnl.score(mg.MG_WANT_SVR)
+        dense_ms = reduce_max(ctx.timer_stop()) / 3
+        td = ctx.timings()
+        ctx.set_svr_mode(0)
+        dense = (dense_ms, td)
+    barrier()
+
     if rank == 0:
         peak, peak_src = fp64_peak_tflops()
         svr_ms_per_launch = tm.ms_svr / max(tm.launches_svr, 1)
         cand_per_launch = tm.candidates_svr / max(tm.launches_svr, 1)
-        achieved = cand_per_launch * FLOP_PER_CAND_PER_SV * N_SV / (svr_ms_per_launch / 1e3) / 1e12
+        dense_equiv = cand_per_launch * FLOP_PER_CAND_PER_SV * N_SV / (svr_ms_per_launch / 1e3) / 1e12
+        # FP64 work the launches really issued (DMMA and DFMA share one pipe on B200): 512 flop per DMMA,
+        # ~19 FP64 instructions (counted as FMA = 2 flop) per exp epilogue element, 2 FMA per gathered triple
+        issued_flop = tm.svr_dmma * 512.0 + tm.svr_exp * 38.0 + tm.svr_gather * 4.0
+        achieved = issued_flop / (tm.ms_svr / 1e3) / 1e12
+        factored = tm.svr_gather > 0
         traffic = None
         tp = os.path.join(ROOT, "profiles", "svr_traffic.json")
         if os.path.exists(tp):
@@ -320,12 +342,26 @@ def main():
                     "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms, "api": "mg_score_regions (host buffers, pinned outputs)"},
             "gpu_launches": launches,
             "kernel_ms_per_step": {"k_feat": tm.ms_feat / args.steps, "k_svr": tm.ms_svr / args.steps, "other": tm.ms_other / args.steps},
-            "roofline": {"kernel": "k_svr_dmma", "bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
-                         "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
-                         "algorithmic_flop_per_candidate": FLOP_PER_CAND_PER_SV * N_SV, "candidates_per_launch": cand_per_launch,
-                         "ms_per_launch": svr_ms_per_launch},
+            "roofline": {"kernel": "k_svr_fact" if factored else "k_svr_dmma", "bound": "tensor", "achieved": achieved, "peak": peak,
+                         "unit": "TFLOP/s", "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+                         "what": "FP64 pipe (DMMA.8x8x4 + the exp/gather DFMAs share it): flop actually issued by the K-svr launches "
+                                 "(512 per DMMA, 38 per exp element, 4 per gathered triple) over their CUDA-event time",
+                         "issued_flop_per_step": issued_flop / args.steps, "dmma_share_of_issued": tm.svr_dmma * 512.0 / issued_flop,
+                         "algorithmic_flop_per_candidate": FLOP_PER_CAND_PER_SV * N_SV,
+                         "dense_equivalent_tflops": dense_equiv,
+                         "note": ("the factored kernel evaluates the same decision function with ~%.1fx less FP64 work than the dense "
+                                  "2*192*N_sv contraction, so the dense-equivalent rate exceeds the pipe's peak"
+                                  % (cand_per_launch * FLOP_PER_CAND_PER_SV * N_SV * tm.launches_svr / issued_flop)) if factored else None,
+                         "candidates_per_launch": cand_per_launch, "ms_per_launch": svr_ms_per_launch},
             "clocks": clocks, "checksum": checksum,
         }
+        if dense is not None:
+            dense_ms, td = dense
+            d_ach = td.svr_dmma * 512.0 / (td.ms_svr / 1e3) / 1e12
+            line["dense_kernel"] = {"kernel": "k_svr_dmma", "value": total_cand / (dense_ms / 1e3), "unit": "candidates/s",
+                                    "ms_per_step": dense_ms, "roofline": {"bound": "tensor", "achieved": d_ach, "peak": peak,
+                                                                          "unit": "TFLOP/s", "frac": d_ach / peak},
+                                    "note": "same panel through the dense candidates x SV contraction (mg_set_svr_mode(1))"}
         if not args.no_cpu_baseline and world == 1:
             line["cpu_baseline"] = cpu_baseline(cfg, model_path, regions[0].lrc, genome)
         print(json.dumps(line))

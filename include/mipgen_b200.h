@@ -98,6 +98,10 @@ typedef struct {
     double ms_svr;   long launches_svr;    /* K-svr  (FP64 DMMA contraction + exp)     */
     double ms_other; long launches_other;  /* encode / lrc / misc                      */
     long candidates_feat, candidates_svr;  /* units the timed launches processed       */
+    /* work actually issued by the K-svr launches (either form), for the roofline:          */
+    double svr_dmma;  /* DMMA.8x8x4 warp instructions (256 FP64 FMA each)                    */
+    double svr_exp;   /* kernel values exp(-gamma d) evaluated                               */
+    double svr_gather;/* factor triples multiplied and accumulated (factored form only)      */
 } mg_timings;
 
 /* ---- context ---------------------------------------------------------------- */

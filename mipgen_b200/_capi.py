@@ -45,7 +45,8 @@ class MgCandidate(C.Structure):
 class MgTimings(C.Structure):
     _fields_ = [("ms_feat", C.c_double), ("launches_feat", C.c_long), ("ms_svr", C.c_double),
                 ("launches_svr", C.c_long), ("ms_other", C.c_double), ("launches_other", C.c_long),
-                ("candidates_feat", C.c_long), ("candidates_svr", C.c_long)]
+                ("candidates_feat", C.c_long), ("candidates_svr", C.c_long),
+                ("svr_dmma", C.c_double), ("svr_exp", C.c_double), ("svr_gather", C.c_double)]
 
 
 # every symbol include/mipgen_b200.h declares: (name, restype, argtypes)

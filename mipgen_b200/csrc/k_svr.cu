@@ -297,6 +297,9 @@ int launch_svr(mg_ctx *ctx, const double *d_x, int64_t n, const uint8_t *d_valid
                                                                        ctx->gamma, ctx->rho, d_valid, d_out);
     mg_time_end(ctx);
     CUDA_TRY(ctx, cudaGetLastError());
+    // executed work: every tile contracts 64 rows x n_sv_pad columns x 192
+    ctx->tm.svr_dmma += (double)tiles * (ctx->n_sv_pad / SVR_BN) * (SVR_BM * SVR_BN * MG_NFEAT / 256.0);
+    ctx->tm.svr_exp += (double)tiles * SVR_BM * ctx->n_sv_pad;
     return MG_OK;
 }
 

@@ -15,8 +15,9 @@
 // distinct rows (defaults: 57*W candidates vs 12*W + 12*(W+5) + 6*W rows).  So per window and per
 // chunk of 16 support vectors the kernel
 //   1. contracts only the DISTINCT rows' blocks with the SV chunk on the FP64 tensor pipe
-//      (DMMA.8x8x4, K = 24 / 40 / 88 instead of 192), turns the distances into kernel factors with
-//      the fused exp epilogue and parks them in three small shared-memory tables;
+//      (DMMA.8x8x4, K = 24 / 24 / 88 instead of 192; the 16 junction one-hot columns of the ligation
+//      block reduce to one table add), turns the distances into kernel factors with the fused exp
+//      epilogue and parks them in three small shared-memory tables;
 //   2. gives every candidate one thread that adds  sum_i  E_a[ra][i] * E_q[rq][i] * E_ins'[ri][i]
 //      to its running score (E_ins' already carries alpha_i * exp(-g d_lrc(region, i))).
 // Same FP64 arithmetic as the dense kernel per block (||x||^2 + ||s||^2 - 2 x.s), ~1e-13 relative
@@ -102,6 +103,16 @@ __global__ void __launch_bounds__(256) k_lrc_weights(const double *__restrict__ 
     }
 }
 
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+// Warp roles: warps [0, kMathWarps) build the factor tables of chunk c+1 on the FP64 pipe while
+// warps [kMathWarps, 2 kMathWarps) gather chunk c through the LSU; one more warp feeds the SV blobs.
+constexpr int kMathWarps = FACT_MATH_WARPS, kGatherWarps = FACT_GATHER_WARPS, kGatherThreads = kGatherWarps * 32, kCpt = FACT_CPT;
+constexpr int kUnitsPerWarp = 24;
+
 __global__ void __launch_bounds__(kThreads, 1)
 k_svr_fact(const DevFact *__restrict__ fc, const DevFTask *__restrict__ tasks, int task0, const double *__restrict__ x, int64_t g_base,
            const uint8_t *__restrict__ valid, const double *__restrict__ blob, const double *__restrict__ w_lrc,
@@ -115,8 +126,7 @@ k_svr_fact(const DevFact *__restrict__ fc, const DevFTask *__restrict__ tasks, i
     const int dsum = fc->max_sum - fc->min_sum;
     // role of the two arm tables on this strand
     const int nA = strand ? n_lig : n_ext, nQ = strand ? n_ext : n_lig;
-    const int ldA = strand ? FACT_LD_LIG : FACT_LD_EXT, ldQ = strand ? FACT_LD_EXT : FACT_LD_LIG;
-    const int kA = strand ? FACT_K_LIG : FACT_K_EXT, kQ = strand ? FACT_K_EXT : FACT_K_LIG;
+    const bool ligA = strand != 0, ligQ = strand == 0;  // which arm table plays the ligation role
     const int RA = (tk.nsi * nA + 7) & ~7, RQ = ((tk.nsi + dsum) * nQ + 7) & ~7, RI = (tk.nsi * n_sums + 7) & ~7;
     const int R = RA + RQ + RI;
 
@@ -125,151 +135,229 @@ k_svr_fact(const DevFact *__restrict__ fc, const DevFTask *__restrict__ tasks, i
     double *FQ = FA + fc->cap_FA;
     double *FI = FQ + fc->cap_FQ;
     double *xx = FI + fc->cap_FI;           // [cap_R]
-    double *E = xx + fc->cap_R;             // [cap_R][EST]
-    double *slab = E + fc->cap_R * EST;     // [2][FACT_BLOB]
+    double *E = xx + fc->cap_R;             // [2][cap_R][EST]  factor tables, double buffered
+    double *slab = E + 2 * fc->cap_R * EST; // [2][FACT_BLOB]
     double *wst = slab + 2 * FACT_BLOB;     // [2][C] alpha_i * exp(-g d_lrc)
     double *etab = wst + 2 * C;             // [64]
-    uint64_t *full = reinterpret_cast<uint64_t *>(etab + 64);  // [2]
-    int *rep = reinterpret_cast<int *>(full + 2);              // [cap_R]
+    uint64_t *bars = reinterpret_cast<uint64_t *>(etab + 64);
+    uint64_t *slab_full = bars, *slab_empty = bars + 2, *e_full = bars + 4, *e_empty = bars + 6;
+    int *rep = reinterpret_cast<int *>(bars + 8);              // [cap_R]
+    int *jc = rep + fc->cap_R;                                 // [cap_R] junction code of ligation-role rows (16: none)
+    uint8_t *unit_list = reinterpret_cast<uint8_t *>(jc + fc->cap_R);  // [kMathWarps][kUnitsPerWarp] units of each math warp
+    uint8_t *unit_cnt = unit_list + kMathWarps * kUnitsPerWarp;        // [kMathWarps]
 
     const int n_c = tk.nsi * n_pairs;  // candidates of this task (one strand, one capture size)
     const int n_chunks = n_sv_pad / C;
     const double *w_reg = w_lrc + (int64_t)tk.region * n_sv_pad;
+    const int ESZ = fc->cap_R * EST;
 
     if (threadIdx.x < 64) etab[threadIdx.x] = exp2_tab[threadIdx.x];
     if (threadIdx.x == 0) {
-        mbar_init(&full[0], 1);
-        mbar_init(&full[1], 1);
+        for (int b = 0; b < 2; b++) {
+            mbar_init(&slab_full[b], 1);
+            mbar_init(&slab_empty[b], kMathWarps);
+            mbar_init(&e_full[b], kMathWarps);
+            mbar_init(&e_empty[b], kGatherWarps);
+        }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     for (int i = threadIdx.x; i < R; i += kThreads) rep[i] = 0x7fffffff;
     __syncthreads();
-    if (threadIdx.x == 0) {  // chunk 0 is in flight while the row tables are built
-        mbar_arrive_expect_tx(&full[0], FACT_BLOB * 8 + C * 8);
-        bulk_g2s(slab, blob, FACT_BLOB * 8, &full[0]);
-        bulk_g2s(wst, w_reg, C * 8, &full[0]);
-    }
 
-    // ---- phase 0: every candidate names its three rows; the lowest candidate index represents a row ----
-    int ra = 0, rq = 0, ri = 0, state = 0;  // state: 0 skipped, 1 invalid (zero row), 2 scored
-    int64_t g = 0;
-    double acc = 0.0;
-    const bool mine = (int)threadIdx.x < n_c;
-    if (mine) {
-        const int s_rel = threadIdx.x / n_pairs, p = threadIdx.x - s_rel * n_pairs;
-        g = tk.g0 + ((((int64_t)(tk.si0 + s_rel) * n_cap + tk.ci) * n_pairs + p) * 2 + strand);
-        const int e = fc->pair_e[p], l = fc->pair_l[p], sum = e + l;
-        const int ie = fc->ext_idx[e], il = fc->lig_idx[l];
-        ra = strand ? s_rel * n_lig + il : s_rel * n_ext + ie;
-        rq = RA + (strand ? (s_rel + fc->max_sum - sum) * n_ext + ie : (s_rel + fc->max_sum - sum) * n_lig + il);
-        ri = RA + RQ + s_rel * n_sums + fc->sum_idx[sum - fc->min_sum];
-        if (valid[g]) {
-            // feature 22 (extension_arm_length) is zero only in the all-zero row of an invalid candidate
-            state = x[(g - g_base) * MG_NFEAT + 21] == 0.0 ? 1 : 2;
-            if (state == 2) {
-                atomicMin(&rep[ra], (int)threadIdx.x);
-                atomicMin(&rep[rq], (int)threadIdx.x);
-                atomicMin(&rep[ri], (int)threadIdx.x);
+    // ---- phase 0 (gather threads): every candidate names its three rows; the lowest candidate index
+    //      represents a row.  Thread t owns candidates t, t + kGatherThreads, ... ----
+    const bool gatherer = warp >= kMathWarps && warp < kMathWarps + kGatherWarps;
+    const int gt = threadIdx.x - kMathWarps * 32;
+    int ra[kCpt], rq[kCpt], ri[kCpt], state[kCpt];  // state: 0 skipped, 1 invalid (zero row), 2 scored
+    int64_t g[kCpt];
+#pragma unroll
+    for (int h = 0; h < kCpt; h++) { ra[h] = rq[h] = ri[h] = state[h] = 0; g[h] = 0; }
+    if (gatherer) {
+#pragma unroll
+        for (int h = 0; h < kCpt; h++) {
+            const int t = gt + h * kGatherThreads;
+            if (t >= n_c) continue;
+            const int s_rel = t / n_pairs, p = t - s_rel * n_pairs;
+            g[h] = tk.g0 + ((((int64_t)(tk.si0 + s_rel) * n_cap + tk.ci) * n_pairs + p) * 2 + strand);
+            const int e = fc->pair_e[p], l = fc->pair_l[p], sum = e + l;
+            const int ie = fc->ext_idx[e], il = fc->lig_idx[l];
+            ra[h] = strand ? s_rel * n_lig + il : s_rel * n_ext + ie;
+            rq[h] = RA + (strand ? (s_rel + fc->max_sum - sum) * n_ext + ie : (s_rel + fc->max_sum - sum) * n_lig + il);
+            ri[h] = RA + RQ + s_rel * n_sums + fc->sum_idx[sum - fc->min_sum];
+            if (valid[g[h]]) {
+                // feature 22 (extension_arm_length) is zero only in the all-zero row of an invalid candidate
+                state[h] = x[(g[h] - g_base) * MG_NFEAT + 21] == 0.0 ? 1 : 2;
+                if (state[h] == 2) {
+                    atomicMin(&rep[ra[h]], t);
+                    atomicMin(&rep[rq[h]], t);
+                    atomicMin(&rep[ri[h]], t);
+                }
             }
         }
+    }
+    // work units of the math warps: one 8-row fragment x all C columns; longest-processing-time assignment
+    const int uI = RI >> 3, uQ = RQ >> 3, uA = RA >> 3, n_units = uI + uQ + uA;
+    if (threadIdx.x == 0) {
+        int load[kMathWarps], cnt[kMathWarps];
+        for (int w = 0; w < kMathWarps; w++) load[w] = cnt[w] = 0;
+        for (int u = 0; u < n_units; u++) {  // units are ordered insert (heavy) first
+            int best = -1;
+            for (int w = 0; w < kMathWarps; w++)
+                if (cnt[w] < kUnitsPerWarp && (best < 0 || load[w] < load[best])) best = w;
+            unit_list[best * kUnitsPerWarp + cnt[best]++] = (uint8_t)u;
+            load[best] += (u < uI ? FACT_K_INS : FACT_K_ARM) + 24;  // k-steps + epilogue
+        }
+        for (int w = 0; w < kMathWarps; w++) unit_cnt[w] = (uint8_t)cnt[w];
     }
     __syncthreads();
 
     // ---- phase 1: copy each row's block out of its representative's feature row; ||row||^2 ----
     for (int row = warp; row < R; row += kWarps) {
         const int t = rep[row];
-        int ld, kk, role;  // role 0 ext, 1 lig, 2 ins
+        int ld, role;  // role 0 ext, 1 lig, 2 ins
         double *dst;
-        if (row < RA) { ld = ldA; kk = kA; role = strand ? 1 : 0; dst = FA + row * ldA; }
-        else if (row < RA + RQ) { ld = ldQ; kk = kQ; role = strand ? 0 : 1; dst = FQ + (row - RA) * ldQ; }
-        else { ld = FACT_LD_INS; kk = FACT_K_INS; role = 2; dst = FI + (row - RA - RQ) * FACT_LD_INS; }
+        if (row < RA) { ld = FACT_LD_ARM; role = ligA ? 1 : 0; dst = FA + row * FACT_LD_ARM; }
+        else if (row < RA + RQ) { ld = FACT_LD_ARM; role = ligQ ? 1 : 0; dst = FQ + (row - RA) * FACT_LD_ARM; }
+        else { ld = FACT_LD_INS; role = 2; dst = FI + (row - RA - RQ) * FACT_LD_INS; }
         const double *src = nullptr;
         if (t != 0x7fffffff) {
             const int s_rel = t / n_pairs, p = t - s_rel * n_pairs;
             const int64_t gr = tk.g0 + ((((int64_t)(tk.si0 + s_rel) * n_cap + tk.ci) * n_pairs + p) * 2 + strand);
             src = x + (gr - g_base) * MG_NFEAT;
         }
-        double ssum = 0.0;
-        for (int k0 = 0; k0 < ld; k0 += 32) {
-            const int k = k0 + lane;
-            double v = 0.0;
-            if (src && k < kk) {
-                if (role == 0) v = k < 22 ? src[k] : (k == 22 ? src[190] : 0.0);
-                else if (role == 1) v = k < 38 ? src[152 + k] : (k == 38 ? src[191] : 0.0);
-                else v = k < 86 ? src[66 + k] : 0.0;
+        double ssum = 0.0, v[3];
+#pragma unroll
+        for (int i = 0; i < 3; i++) {
+            const int k = i * 32 + lane;
+            v[i] = 0.0;
+            if (src && k < ld) {
+                if (role == 0) v[i] = k < 22 ? src[k] : (k == 22 ? src[190] : 0.0);
+                else if (role == 1) v[i] = k < 22 ? src[152 + k] : (k == 22 ? src[191] : 0.0);
+                else v[i] = k < 86 ? src[66 + k] : 0.0;
             }
-            if (k < ld) dst[k] = v;
-            ssum = fma(v, v, ssum);
+            ssum = fma(v[i], v[i], ssum);
         }
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) ssum += __shfl_xor_sync(0xffffffffu, ssum, o);
-        if (lane == 0) xx[row] = ssum;
+        // a non-finite feature (log10(0) = -inf copy) makes every kernel value of the row 0, as in libsvm:
+        // park the row at distance +inf with finite (zero) features so the contraction stays NaN free
+        const bool finite = fabs(ssum) <= 1.7976931348623157e308;
+#pragma unroll
+        for (int i = 0; i < 3; i++) {
+            const int k = i * 32 + lane;
+            if (k < ld) dst[k] = finite ? v[i] : 0.0;
+        }
+        if (lane == 0) xx[row] = finite ? ssum : __longlong_as_double(0x7ff0000000000000LL);
+        if (role == 1) {
+            // junction one-hot 175..190 -> code
+            int code = 16;
+            if (src && lane < 16 && src[174 + lane] == 1.0) code = lane;
+#pragma unroll
+            for (int o = 8; o > 0; o >>= 1) code = min(code, __shfl_xor_sync(0xffffffffu, code, o));
+            if (lane == 0) jc[row] = code;
+        } else if (lane == 0) jc[row] = 16;
     }
     __syncthreads();
 
-    // ---- main loop over chunks of C support vectors ----
     const double ngamma = -gamma;
-    const int uI = RI >> 3, uQ = RQ >> 3, uA = RA >> 3, n_units = uI + uQ + uA;
-    for (int ch = 0; ch < n_chunks; ch++) {
-        const int st = ch & 1;
-        if (threadIdx.x == 0 && ch + 1 < n_chunks) {  // prefetch the next chunk into the other stage
-            mbar_arrive_expect_tx(&full[st ^ 1], FACT_BLOB * 8 + C * 8);
-            bulk_g2s(slab + (st ^ 1) * FACT_BLOB, blob + (int64_t)(ch + 1) * FACT_BLOB, FACT_BLOB * 8, &full[st ^ 1]);
-            bulk_g2s(wst + (st ^ 1) * C, w_reg + (int64_t)(ch + 1) * C, C * 8, &full[st ^ 1]);
-        }
-        mbar_wait(&full[st], (ch >> 1) & 1);
-        const double *sb = slab + st * FACT_BLOB;
-        const double *ws = wst + st * C;
-
-        // (1) kernel factors of the distinct rows: DMMA over the row's block, fused exp epilogue.
-        //     unit = one 8-row fragment x all C columns; largest units (insert, K=88) first.
-        for (int u = warp; u < n_units; u += kWarps) {
-            const double *F, *S, *ssb;
-            int ld, ksteps, row0;
-            bool is_ins = false;
-            if (u < uI) { F = FI + (u * 8) * FACT_LD_INS; ld = FACT_LD_INS; ksteps = FACT_K_INS / 4; S = sb + FACT_OFF_INS; ssb = sb + FACT_OFF_SS + 2 * C; row0 = RA + RQ + u * 8; is_ins = true; }
-            else if (u < uI + uQ) {
-                const int m = u - uI;
-                F = FQ + (m * 8) * ldQ; ld = ldQ; ksteps = kQ / 4; row0 = RA + m * 8;
-                S = sb + (strand ? FACT_OFF_EXT : FACT_OFF_LIG); ssb = sb + FACT_OFF_SS + (strand ? 0 : C);
-            } else {
-                const int m = u - uI - uQ;
-                F = FA + (m * 8) * ldA; ld = ldA; ksteps = kA / 4; row0 = m * 8;
-                S = sb + (strand ? FACT_OFF_LIG : FACT_OFF_EXT); ssb = sb + FACT_OFF_SS + (strand ? C : 0);
+    if (warp == kMathWarps + kGatherWarps) {
+        // =============================== producer warp: SV blobs ===============================
+        if (lane == 0) {
+            for (int ch = 0; ch < n_chunks; ch++) {
+                const int st = ch & 1;
+                if (ch >= 2) mbar_wait(&slab_empty[st], ((ch >> 1) & 1) ^ 1);
+                mbar_arrive_expect_tx(&slab_full[st], FACT_BLOB * 8 + C * 8);
+                bulk_g2s(slab + st * FACT_BLOB, blob + (int64_t)ch * FACT_BLOB, FACT_BLOB * 8, &slab_full[st]);
+                bulk_g2s(wst + st * C, w_reg + (int64_t)ch * C, C * 8, &slab_full[st]);
             }
-            double a0[2] = {0.0, 0.0}, a1[2] = {0.0, 0.0};
-            const double *fa = F + gid * ld + tig, *s0 = S + gid * ld + tig, *s1 = S + (8 + gid) * ld + tig;
+        }
+    } else if (warp < kMathWarps) {
+        // ======================= math warps: factor tables of the distinct rows =======================
+        const int my_units = unit_cnt[warp];
+        for (int ch = 0; ch < n_chunks; ch++) {
+            const int st = ch & 1;
+            mbar_wait(&slab_full[st], (ch >> 1) & 1);
+            if (ch >= 2) mbar_wait(&e_empty[st], ((ch >> 1) & 1) ^ 1);
+            const double *sb = slab + st * FACT_BLOB;
+            const double *ws = wst + st * C;
+            double *Eb = E + st * ESZ;
+            for (int ui = 0; ui < my_units; ui++) {
+                const int u = unit_list[warp * kUnitsPerWarp + ui];
+                const double *F, *S, *ssb;
+                int ld, ksteps, row0;
+                bool is_ins = false, is_lig;
+                if (u < uI) {
+                    F = FI + (u * 8) * FACT_LD_INS; ld = FACT_LD_INS; ksteps = FACT_K_INS / 4; S = sb + FACT_OFF_INS;
+                    ssb = sb + FACT_OFF_SS + 2 * C; row0 = RA + RQ + u * 8; is_ins = true; is_lig = false;
+                } else if (u < uI + uQ) {
+                    const int m = u - uI;
+                    F = FQ + (m * 8) * FACT_LD_ARM; ld = FACT_LD_ARM; ksteps = FACT_K_ARM / 4; row0 = RA + m * 8; is_lig = ligQ;
+                    S = sb + (is_lig ? FACT_OFF_LIG : FACT_OFF_EXT); ssb = sb + FACT_OFF_SS + (is_lig ? C : 0);
+                } else {
+                    const int m = u - uI - uQ;
+                    F = FA + (m * 8) * FACT_LD_ARM; ld = FACT_LD_ARM; ksteps = FACT_K_ARM / 4; row0 = m * 8; is_lig = ligA;
+                    S = sb + (is_lig ? FACT_OFF_LIG : FACT_OFF_EXT); ssb = sb + FACT_OFF_SS + (is_lig ? C : 0);
+                }
+                // 4 independent accumulator chains: 2 column fragments x even/odd k-steps
+                double a[2][2] = {{0.0, 0.0}, {0.0, 0.0}}, b[2][2] = {{0.0, 0.0}, {0.0, 0.0}};
+                const double *fa = F + gid * ld + tig, *s0 = S + gid * ld + tig, *s1 = S + (8 + gid) * ld + tig;
 #pragma unroll 2
-            for (int ks = 0; ks < ksteps; ks++) {
-                const double a = fa[ks * 4], b0 = s0[ks * 4], b1 = s1[ks * 4];
-                dmma884(a0[0], a0[1], a, b0);
-                dmma884(a1[0], a1[1], a, b1);
-            }
-            const double xr = xx[row0 + gid];
-            const bool finite = fabs(xr) <= 1.7976931348623157e308;  // -inf copy feature: every factor is 0
-            double *er = E + (row0 + gid) * EST;
+                for (int ks = 0; ks < ksteps; ks += 2) {
+                    const double f0 = fa[ks * 4], f1 = fa[ks * 4 + 4];
+                    dmma884(a[0][0], a[0][1], f0, s0[ks * 4]);
+                    dmma884(a[1][0], a[1][1], f0, s1[ks * 4]);
+                    dmma884(b[0][0], b[0][1], f1, s0[ks * 4 + 4]);
+                    dmma884(b[1][0], b[1][1], f1, s1[ks * 4 + 4]);
+                }
+                const int row = row0 + gid;
+                const double base = xx[row];
+                const double *jt = sb + FACT_OFF_JT + (is_lig ? jc[row] : 16) * C;
+                double *er = Eb + row * EST;
 #pragma unroll
-            for (int j = 0; j < 2; j++) {
-                const int c0 = 2 * tig + j, c1 = 8 + 2 * tig + j;
-                double d0 = fmax(fma(-2.0, a0[j], xr + ssb[c0]), 0.0), d1 = fmax(fma(-2.0, a1[j], xr + ssb[c1]), 0.0);
-                double e0 = finite ? exp_nonpos(ngamma * d0, etab) : 0.0, e1 = finite ? exp_nonpos(ngamma * d1, etab) : 0.0;
-                if (is_ins) { e0 *= ws[c0]; e1 *= ws[c1]; }
-                er[c0] = e0;
-                er[c1] = e1;
+                for (int nf = 0; nf < 2; nf++) {
+                    const int c0 = nf * 8 + 2 * tig;
+                    const double d0 = fmax(fma(-2.0, a[nf][0] + b[nf][0], base + ssb[c0] + jt[c0]), 0.0);
+                    const double d1 = fmax(fma(-2.0, a[nf][1] + b[nf][1], base + ssb[c0 + 1] + jt[c0 + 1]), 0.0);
+                    double e0 = exp_nonpos(ngamma * d0, etab), e1 = exp_nonpos(ngamma * d1, etab);
+                    if (is_ins) { e0 *= ws[c0]; e1 *= ws[c0 + 1]; }
+                    er[c0] = e0;
+                    er[c0 + 1] = e1;
+                }
+            }
+            __syncwarp();
+            if (lane == 0) {
+                mbar_arrive(&e_full[st]);      // this warp's rows of chunk ch are in the table
+                mbar_arrive(&slab_empty[st]);  // and it no longer reads the SV blob of chunk ch
             }
         }
-        __syncthreads();
-
-        // (2) every candidate gathers its three factors
-        if (state == 2) {
-            const double *ea = E + ra * EST, *eq = E + rq * EST, *ei = E + ri * EST;
+    } else {
+        // ======================= gather warps: every candidate picks its three factors =======================
+        double acc[kCpt];
 #pragma unroll
-            for (int i = 0; i < C; i++) acc = fma(ea[i] * eq[i], ei[i], acc);
+        for (int h = 0; h < kCpt; h++) acc[h] = 0.0;
+        for (int ch = 0; ch < n_chunks; ch++) {
+            const int st = ch & 1;
+            mbar_wait(&e_full[st], (ch >> 1) & 1);
+            const double *Eb = E + st * ESZ;
+#pragma unroll
+            for (int h = 0; h < kCpt; h++) {
+                if (state[h] != 2) continue;
+                const double *ea = Eb + ra[h] * EST, *eq = Eb + rq[h] * EST, *ei = Eb + ri[h] * EST;
+                double s = acc[h];
+#pragma unroll
+                for (int i = 0; i < C; i++) s = fma(ea[i] * eq[i], ei[i], s);
+                acc[h] = s;
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&e_empty[st]);
         }
-        __syncthreads();
+#pragma unroll
+        for (int h = 0; h < kCpt; h++) {
+            const int t = gt + h * kGatherThreads;
+            if (t < n_c)
+                out[g[h]] = state[h] == 2 ? acc[h] - rho : (state[h] == 1 ? zero_score : __longlong_as_double(0x7ff8000000000000LL));
+        }
     }
-
-    if (mine) out[g] = state == 2 ? acc - rho : (state == 1 ? zero_score : __longlong_as_double(0x7ff8000000000000LL));
 }
 
 }  // namespace
@@ -299,5 +387,21 @@ int launch_svr_fact(mg_ctx *ctx, const mg_panel *p, int ftask0, int ftask1, cons
                                                                          ctx->rho, ctx->zero_score, d_out);
     mg_time_end(ctx);
     CUDA_TRY(ctx, cudaGetLastError());
+    // executed work, from the task list: rows are padded to 8, every 8-row fragment meets C columns
+    {
+        const HostConfig &h = ctx->cfg;
+        const DevFact &f = ctx->h_fact;
+        const double chunks = ctx->n_sv_pad / FACT_C;
+        double dmma = 0, ex = 0, ga = 0;
+        for (int t = ftask0; t < ftask1; t++) {
+            const DevFTask &tk = p->h_ftasks[t];
+            const int nA = tk.strand ? f.n_lig : f.n_ext, nQ = tk.strand ? f.n_ext : f.n_lig;
+            const int RA = (tk.nsi * nA + 7) & ~7, RQ = ((tk.nsi + h.max_sum - h.min_sum) * nQ + 7) & ~7, RI = (tk.nsi * f.n_sums + 7) & ~7;
+            dmma += chunks * ((RA + RQ) / 8 * (FACT_K_ARM / 4) + RI / 8 * (FACT_K_INS / 4)) * (FACT_C / 8);
+            ex += chunks * (RA + RQ + RI) * FACT_C;
+            ga += chunks * tk.nsi * f.n_pairs * FACT_C;
+        }
+        ctx->tm.svr_dmma += dmma; ctx->tm.svr_exp += ex; ctx->tm.svr_gather += ga;
+    }
     return MG_OK;
 }

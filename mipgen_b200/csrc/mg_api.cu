@@ -359,20 +359,21 @@ extern "C" int mg_set_config(mg_ctx *ctx, const mg_config *c)
             const int dsum = h.max_sum - h.min_sum;
             auto pad8 = [](int v) { return (v + 7) & ~7; };
             for (int W = 8; W >= 1 && !ctx->fact_ok; W /= 2) {
-                if (W * c->n_pairs > FACT_THREADS) continue;
+                if (W * c->n_pairs > FACT_CPT * FACT_GATHER_WARPS * 32) continue;  // FACT_CPT candidates per gather thread
                 const int RA0 = pad8(W * f->n_ext), RA1 = pad8(W * f->n_lig);
                 const int RQ0 = pad8((W + dsum) * f->n_lig), RQ1 = pad8((W + dsum) * f->n_ext), RI = pad8(W * f->n_sums);
-                f->cap_FA = std::max(RA0 * FACT_LD_EXT, RA1 * FACT_LD_LIG);
-                f->cap_FQ = std::max(RQ0 * FACT_LD_LIG, RQ1 * FACT_LD_EXT);
+                f->cap_FA = std::max(RA0, RA1) * FACT_LD_ARM;
+                f->cap_FQ = std::max(RQ0, RQ1) * FACT_LD_ARM;
                 f->cap_FI = RI * FACT_LD_INS;
                 f->cap_R = std::max(RA0 + RQ0, RA1 + RQ1) + RI;
-                size_t doubles = (size_t)f->cap_FA + f->cap_FQ + f->cap_FI + f->cap_R + (size_t)f->cap_R * (FACT_C + 1) + 2 * FACT_BLOB +
+                if (f->cap_R / 8 > FACT_MATH_WARPS * 24) continue;  // per-warp work-unit lists
+                size_t doubles = (size_t)f->cap_FA + f->cap_FQ + f->cap_FI + f->cap_R + 2 * (size_t)f->cap_R * (FACT_C + 1) + 2 * FACT_BLOB +
                                  2 * FACT_C + 64;
-                size_t bytes = doubles * 8 + 16 + (size_t)f->cap_R * 4 + 64;
+                size_t bytes = doubles * 8 + 64 + (size_t)f->cap_R * 8 + FACT_MATH_WARPS * 25 + 64;  // + mbarriers, rep[] and jc[] ints, unit lists
                 if (bytes <= FACT_SMEM_LIMIT) { f->W = W; ctx->fact_ok = true; ctx->fact_W = W; ctx->fact_smem = bytes; }
             }
         }
-        if (ctx->fact_ok) e = cudaMemcpy(ctx->d_fact, f, sizeof *f, cudaMemcpyHostToDevice);
+        if (ctx->fact_ok) { e = cudaMemcpy(ctx->d_fact, f, sizeof *f, cudaMemcpyHostToDevice); ctx->h_fact = *f; }
         delete f;
         if (e != cudaSuccess) { ctx->err = std::string("factored config upload: ") + cudaGetErrorString(e); return MG_ERR_CUDA; }
     }
@@ -429,10 +430,13 @@ static int upload_model(mg_ctx *ctx, const std::vector<double> &dense, const std
             const int r = i % FACT_C;
             const double *srow = &sv[(size_t)i * MG_NFEAT];
             double se = 0, sl = 0, si = 0;
-            for (int k = 0; k < 22; k++) { b[FACT_OFF_EXT + r * FACT_LD_EXT + k] = srow[k]; se += srow[k] * srow[k]; }
-            b[FACT_OFF_EXT + r * FACT_LD_EXT + 22] = srow[190]; se += srow[190] * srow[190];
-            for (int k = 0; k < 38; k++) { b[FACT_OFF_LIG + r * FACT_LD_LIG + k] = srow[152 + k]; sl += srow[152 + k] * srow[152 + k]; }
-            b[FACT_OFF_LIG + r * FACT_LD_LIG + 38] = srow[191]; sl += srow[191] * srow[191];
+            for (int k = 0; k < 22; k++) { b[FACT_OFF_EXT + r * FACT_LD_ARM + k] = srow[k]; se += srow[k] * srow[k]; }
+            b[FACT_OFF_EXT + r * FACT_LD_ARM + 22] = srow[190]; se += srow[190] * srow[190];
+            for (int k = 0; k < 22; k++) { b[FACT_OFF_LIG + r * FACT_LD_ARM + k] = srow[152 + k]; sl += srow[152 + k] * srow[152 + k]; }
+            b[FACT_OFF_LIG + r * FACT_LD_ARM + 22] = srow[191]; sl += srow[191] * srow[191];
+            // junction one-hot (features 175..190): ||onehot(jc) - s||^2 = sum_j s_j^2 + (1 - 2 s_jc)
+            for (int k = 0; k < 16; k++) { sl += srow[174 + k] * srow[174 + k]; b[FACT_OFF_JT + k * FACT_C + r] = 1.0 - 2.0 * srow[174 + k]; }
+            b[FACT_OFF_JT + 16 * FACT_C + r] = 0.0;
             for (int k = 0; k < 86; k++) { b[FACT_OFF_INS + r * FACT_LD_INS + k] = srow[66 + k]; si += srow[66 + k] * srow[66 + k]; }
             b[FACT_OFF_SS + r] = se; b[FACT_OFF_SS + FACT_C + r] = sl; b[FACT_OFF_SS + 2 * FACT_C + r] = si;
         }

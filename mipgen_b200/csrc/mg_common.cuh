@@ -106,18 +106,20 @@ __host__ __device__ inline uint32_t fd_pack(uint32_t kind, uint32_t part, uint32
 // factored SVR (k_svr_fact.cu): block sizes, padded strides, per-chunk blob layout
 // ---------------------------------------------------------------------------
 #define FACT_C 16          // support vectors per chunk
-#define FACT_THREADS 512
-#define FACT_K_EXT 24      // 22 ext features + log copy, padded to a multiple of 4
-#define FACT_K_LIG 40      // 38 lig features + log copy
+#define FACT_MATH_WARPS 12
+#define FACT_GATHER_WARPS 4
+#define FACT_CPT 4                                      // candidates per gather thread
+#define FACT_THREADS ((FACT_MATH_WARPS + FACT_GATHER_WARPS + 1) * 32)   // + 1 producer warp
+#define FACT_K_ARM 24      // 21 arm ratios + arm length + log copy, padded to a multiple of 4 (either role)
 #define FACT_K_INS 88      // 86 insert features
-#define FACT_LD_EXT 28     // strides == 12 mod 16 doubles: conflict-free LDS.64 fragment loads
-#define FACT_LD_LIG 44
+#define FACT_LD_ARM 28     // strides == 12 mod 16 doubles: conflict-free LDS.64 fragment loads
 #define FACT_LD_INS 92
 #define FACT_OFF_EXT 0
-#define FACT_OFF_LIG (FACT_C * FACT_LD_EXT)
-#define FACT_OFF_INS (FACT_OFF_LIG + FACT_C * FACT_LD_LIG)
-#define FACT_OFF_SS (FACT_OFF_INS + FACT_C * FACT_LD_INS)   // ss_ext[C], ss_lig[C], ss_ins[C]
-#define FACT_BLOB (FACT_OFF_SS + 3 * FACT_C)                // doubles per chunk
+#define FACT_OFF_LIG (FACT_C * FACT_LD_ARM)
+#define FACT_OFF_INS (FACT_OFF_LIG + FACT_C * FACT_LD_ARM)
+#define FACT_OFF_SS (FACT_OFF_INS + FACT_C * FACT_LD_INS)   // ss_ext[C], ss_lig[C] (incl. junction columns), ss_ins[C]
+#define FACT_OFF_JT (FACT_OFF_SS + 3 * FACT_C)              // JT[17][C]: 1 - 2 s_i[junction]  (row 16: no junction -> 0)
+#define FACT_BLOB (FACT_OFF_JT + 17 * FACT_C)               // doubles per chunk
 #define FACT_SMEM_LIMIT (227 * 1024)
 #define FACT_MAX_LEN 64
 #define FACT_MAX_SPAN 128
@@ -174,6 +176,7 @@ struct mg_ctx {
     int fact_W = 0;
     size_t fact_smem = 0;
     DevFact *d_fact = nullptr;
+    DevFact h_fact{};               // host copy (work accounting)
     double *d_fact_blob = nullptr;  // [n_sv_pad/FACT_C][FACT_BLOB] per-chunk SV blocks + block norms
     double zero_score = 0;          // SVR value of the all-zero vector (invalid candidates)
     // workspace
