@@ -65,6 +65,65 @@ static void drain_timings(mg_ctx *ctx)
 }
 
 // ---------------------------------------------------------------------------
+// caching device allocator.  All work of a context is ordered on one stream, so a block freed
+// by the host after the calls that used it were enqueued can be handed to later calls at once.
+// ---------------------------------------------------------------------------
+static const size_t kPoolCap = (size_t)12 << 30;
+
+cudaError_t mg_dev_alloc(mg_ctx *ctx, void **out, size_t bytes)
+{
+    if (bytes == 0) bytes = 16;
+    int best = -1;
+    for (size_t i = 0; i < ctx->pool.size(); i++)
+        if (ctx->pool[i].bytes >= bytes && ctx->pool[i].bytes <= bytes + bytes / 2 + 4096 &&
+            (best < 0 || ctx->pool[i].bytes < ctx->pool[best].bytes))
+            best = (int)i;
+    if (best >= 0) {
+        CachedBlock b = ctx->pool[best];
+        ctx->pool.erase(ctx->pool.begin() + best);
+        ctx->pool_bytes -= b.bytes;
+        ctx->live.push_back(b);
+        *out = b.ptr;
+        return cudaSuccess;
+    }
+    cudaError_t e = cudaMalloc(out, bytes);
+    if (e != cudaSuccess) {  // give cached memory back and retry once
+        cudaGetLastError();
+        mg_dev_trim(ctx);
+        e = cudaMalloc(out, bytes);
+    }
+    if (e == cudaSuccess) ctx->live.push_back({*out, bytes});
+    return e;
+}
+
+void mg_dev_free(mg_ctx *ctx, void *ptr)
+{
+    if (!ptr) return;
+    for (size_t i = 0; i < ctx->live.size(); i++)
+        if (ctx->live[i].ptr == ptr) {
+            CachedBlock b = ctx->live[i];
+            ctx->live.erase(ctx->live.begin() + i);
+            if (ctx->pool_bytes + b.bytes <= kPoolCap) {
+                ctx->pool.push_back(b);
+                ctx->pool_bytes += b.bytes;
+            } else {
+                cudaStreamSynchronize(ctx->stream);
+                cudaFree(ptr);
+            }
+            return;
+        }
+    cudaFree(ptr);  // not ours
+}
+
+void mg_dev_trim(mg_ctx *ctx)
+{
+    cudaStreamSynchronize(ctx->stream);
+    for (auto &b : ctx->pool) cudaFree(b.ptr);
+    ctx->pool.clear();
+    ctx->pool_bytes = 0;
+}
+
+// ---------------------------------------------------------------------------
 // static tables
 // ---------------------------------------------------------------------------
 // mipgen.cpp:32 (data): the 44 strand-symmetric k-mers of long_range_content
@@ -222,6 +281,7 @@ extern "C" void mg_destroy(mg_ctx *ctx)
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
     drain_timings(ctx);
+    mg_dev_trim(ctx);
     for (auto e : ctx->ev_free) cudaEventDestroy(e);
     if (ctx->sw_a) { cudaEventDestroy(ctx->sw_a); cudaEventDestroy(ctx->sw_b); }
     free_model(ctx);
@@ -732,10 +792,10 @@ extern "C" void mg_panel_destroy(mg_panel *p)
 {
     if (!p) return;
     cudaSetDevice(p->ctx->device);
-    cudaStreamSynchronize(p->ctx->stream);
-    cudaFree(p->d_ftasks); cudaFree(p->d_w);
-    cudaFree(p->d_regions); cudaFree(p->d_tasks); cudaFree(p->d_codes); cudaFree(p->d_lrc); cudaFree(p->d_copies);
-    cudaFree(p->d_valid); cudaFree(p->d_logistic); cudaFree(p->d_svr); cudaFree(p->d_feat);
+    mg_ctx *c = p->ctx;
+    mg_dev_free(c, p->d_ftasks); mg_dev_free(c, p->d_w);
+    mg_dev_free(c, p->d_regions); mg_dev_free(c, p->d_tasks); mg_dev_free(c, p->d_codes); mg_dev_free(c, p->d_lrc); mg_dev_free(c, p->d_copies);
+    mg_dev_free(c, p->d_valid); mg_dev_free(c, p->d_logistic); mg_dev_free(c, p->d_svr); mg_dev_free(c, p->d_feat);
     delete p;
 }
 
@@ -829,35 +889,35 @@ extern "C" int mg_panel_create(mg_ctx *ctx, const mg_region *regions, int n, mg_
             if (r.copies) memcpy(&cp[p->h_regions[i].copy_off], r.copies, (size_t)n_oligo * r.seq_len * sizeof(int));
         }
         char *d_ascii = nullptr;
-        P_TRY(cudaMalloc(&d_ascii, (size_t)codes));
-        P_TRY(cudaMalloc(&p->d_codes, (size_t)codes));
-        P_TRY(cudaMalloc(&p->d_regions, (size_t)n * sizeof(DevRegion)));
+        P_TRY(mg_dev_alloc(ctx, (void **)&d_ascii, (size_t)codes));
+        P_TRY(mg_dev_alloc(ctx, (void **)&p->d_codes, (size_t)codes));
+        P_TRY(mg_dev_alloc(ctx, (void **)&p->d_regions, (size_t)n * sizeof(DevRegion)));
         P_TRY(cudaMemcpyAsync(d_ascii, ascii.data(), (size_t)codes, cudaMemcpyHostToDevice, ctx->stream));
         P_TRY(cudaMemcpyAsync(p->d_regions, p->h_regions.data(), (size_t)n * sizeof(DevRegion), cudaMemcpyHostToDevice, ctx->stream));
         if (!p->h_ftasks.empty()) {
-            P_TRY(cudaMalloc(&p->d_ftasks, p->h_ftasks.size() * sizeof(DevFTask)));
+            P_TRY(mg_dev_alloc(ctx, (void **)&p->d_ftasks, p->h_ftasks.size() * sizeof(DevFTask)));
             P_TRY(cudaMemcpyAsync(p->d_ftasks, p->h_ftasks.data(), p->h_ftasks.size() * sizeof(DevFTask), cudaMemcpyHostToDevice, ctx->stream));
         }
         if (!p->h_tasks.empty()) {
-            P_TRY(cudaMalloc(&p->d_tasks, p->h_tasks.size() * sizeof(DevTask)));
+            P_TRY(mg_dev_alloc(ctx, (void **)&p->d_tasks, p->h_tasks.size() * sizeof(DevTask)));
             P_TRY(cudaMemcpyAsync(p->d_tasks, p->h_tasks.data(), p->h_tasks.size() * sizeof(DevTask), cudaMemcpyHostToDevice, ctx->stream));
         }
         if (any_lrc) {
-            P_TRY(cudaMalloc(&p->d_lrc, lrc.size() * 8));
+            P_TRY(mg_dev_alloc(ctx, (void **)&p->d_lrc, lrc.size() * 8));
             P_TRY(cudaMemcpyAsync(p->d_lrc, lrc.data(), lrc.size() * 8, cudaMemcpyHostToDevice, ctx->stream));
         }
         if (copies > 0) {
-            P_TRY(cudaMalloc(&p->d_copies, (size_t)copies * sizeof(int)));
+            P_TRY(mg_dev_alloc(ctx, (void **)&p->d_copies, (size_t)copies * sizeof(int)));
             P_TRY(cudaMemcpyAsync(p->d_copies, cp.data(), (size_t)copies * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
         }
         int rc = launch_encode(ctx, d_ascii, p->d_codes, codes);
         cudaStreamSynchronize(ctx->stream);  // host staging vectors go out of scope
-        cudaFree(d_ascii);
+        mg_dev_free(ctx, d_ascii);
         if (rc != MG_OK) { mg_panel_destroy(p); return rc; }
     }
     if (p->n_cand > 0) {
-        P_TRY(cudaMalloc(&p->d_valid, (size_t)p->n_cand));
-        P_TRY(cudaMalloc(&p->d_logistic, (size_t)p->n_cand * 8));
+        P_TRY(mg_dev_alloc(ctx, (void **)&p->d_valid, (size_t)p->n_cand));
+        P_TRY(mg_dev_alloc(ctx, (void **)&p->d_logistic, (size_t)p->n_cand * 8));
     }
 #undef P_TRY
     *out = p;
@@ -873,10 +933,10 @@ extern "C" int mg_panel_score(mg_ctx *ctx, mg_panel *p, int want)
     if (p->n_cand == 0) return MG_OK;
     CUDA_TRY(ctx, cudaSetDevice(ctx->device));
     const bool w_log = want & MG_WANT_LOGISTIC, w_svr = want & MG_WANT_SVR, w_feat = want & MG_WANT_FEATURES;
-    if (w_svr && !p->d_svr) CUDA_TRY(ctx, cudaMalloc(&p->d_svr, (size_t)p->n_cand * 8));
+    if (w_svr && !p->d_svr) CUDA_TRY(ctx, mg_dev_alloc(ctx, (void **)&p->d_svr, (size_t)p->n_cand * 8));
     if (w_feat && !p->d_feat) {
         int64_t rows = (p->n_cand + SVR_BM - 1) / SVR_BM * SVR_BM;
-        CUDA_TRY(ctx, cudaMalloc(&p->d_feat, (size_t)rows * MG_NFEAT * 8));
+        CUDA_TRY(ctx, mg_dev_alloc(ctx, (void **)&p->d_feat, (size_t)rows * MG_NFEAT * 8));
         CUDA_TRY(ctx, cudaMemsetAsync(p->d_feat, 0, (size_t)rows * MG_NFEAT * 8, ctx->stream));
     }
     int rc = MG_OK;
@@ -889,9 +949,9 @@ extern "C" int mg_panel_score(mg_ctx *ctx, mg_panel *p, int want)
     }
     if (fact) {
         if (!p->d_w || p->w_n_sv_pad != ctx->n_sv_pad) {
-            cudaFree(p->d_w);
+            mg_dev_free(ctx, p->d_w);
             p->d_w = nullptr;
-            CUDA_TRY(ctx, cudaMalloc(&p->d_w, (size_t)p->n_regions * ctx->n_sv_pad * 8));
+            CUDA_TRY(ctx, mg_dev_alloc(ctx, (void **)&p->d_w, (size_t)p->n_regions * ctx->n_sv_pad * 8));
             p->w_n_sv_pad = ctx->n_sv_pad;
         }
         if ((rc = launch_lrc_weights(ctx, p, p->d_w)) != MG_OK) return rc;

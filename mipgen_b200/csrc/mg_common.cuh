@@ -147,6 +147,7 @@ struct HostConfig {
 };
 
 struct EventPair { cudaEvent_t a, b; int which; long units; };
+struct CachedBlock { void *ptr; size_t bytes; };
 
 struct mg_ctx {
     int device = 0;
@@ -182,6 +183,10 @@ struct mg_ctx {
     // workspace
     double *d_x = nullptr;      // feature rows of the chunk in flight
     size_t x_rows_cap = 0;
+    // freed device blocks kept for reuse (the per-call buffers of mg_score_regions / mg_score_candidates)
+    std::vector<CachedBlock> pool;
+    std::vector<CachedBlock> live;
+    size_t pool_bytes = 0;
     // timing
     std::vector<EventPair> ev_pending;
     std::vector<cudaEvent_t> ev_free;
@@ -225,6 +230,11 @@ struct mg_panel {
             return MG_ERR_CUDA;                                                              \
         }                                                                                    \
     } while (0)
+
+// caching device allocator (mg_api.cu): stream-ordered reuse on the context's single stream
+cudaError_t mg_dev_alloc(mg_ctx *ctx, void **out, size_t bytes);
+void mg_dev_free(mg_ctx *ctx, void *ptr);
+void mg_dev_trim(mg_ctx *ctx);
 
 // kernels / launchers (defined in k_feat.cu, k_svr.cu)
 enum { TM_FEAT = 0, TM_SVR = 1, TM_OTHER = 2 };
