@@ -195,6 +195,23 @@ k_svr_fact(const DevFact *__restrict__ fc, const DevFTask *__restrict__ tasks, i
             }
         }
     }
+    // a task whose candidates are all skipped or invalid (e.g. a capture size ruled out by mipgen.cpp:429)
+    // has no factor tables to build
+    {
+        int any = 0;
+#pragma unroll
+        for (int h = 0; h < kCpt; h++) any |= state[h] == 2;
+        if (!__syncthreads_or(any)) {
+            if (gatherer) {
+#pragma unroll
+                for (int h = 0; h < kCpt; h++) {
+                    const int t = gt + h * kGatherThreads;
+                    if (t < n_c) out[g[h]] = state[h] == 1 ? zero_score : __longlong_as_double(0x7ff8000000000000LL);
+                }
+            }
+            return;
+        }
+    }
     // work units of the math warps: one 8-row fragment x all C columns; longest-processing-time assignment
     const int uI = RI >> 3, uQ = RQ >> 3, uA = RA >> 3, n_units = uI + uQ + uA;
     if (threadIdx.x == 0) {

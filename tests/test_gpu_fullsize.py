@@ -123,3 +123,88 @@ def test_replay_enumerates_only_valid_points(setup):
         assert pruned.size < full.size and np.all(np.diff(pruned) > 0) and np.isin(pruned, full).all()
         total += pruned.size
     assert total > 0
+
+
+def test_multi_capture_panel_cfg4_style():
+    """BASELINE.json configs[3] shape: capture sweep 120..250 step 5 (27 sizes, 3078 grid points per scan
+    start), short regions so the static capture skip (mipgen.cpp:429) removes many sizes.  Checked through
+    properties + an oracle sample; factored and dense SVR must agree everywhere."""
+    from oracle_api import Oracle
+    from helpers import random_model
+    oracle = Oracle()
+    cfg = panel.Config(250, 120, 5)
+    genome = panel.lcg_genome(40000, 4004)
+    regions = panel.make_regions(genome, 3, 60, 170, cfg, 4005)
+    ctx = mg.Context(0)
+    ctx.set_config(cfg)
+    for r in regions:
+        r.lrc = ctx.long_range_content(r.flank_seq, r.seq_start, r.seq_stop)
+    ctx.load_svr_model(random_model(oracle, panel.Config(), 200, 44, os.path.join(tmpdir(), "m.model")))
+    assert ctx.svr_factored_available() > 0
+    offs, valid, lo, sv, _ = ctx.score_regions(regions, mg.MG_WANT_LOGISTIC | mg.MG_WANT_SVR)
+    ctx.set_svr_mode(1)
+    _o, v2, _l, dense, _f = ctx.score_regions(regions, mg.MG_WANT_SVR)
+    ctx.set_svr_mode(0)
+    assert int(offs[-1]) > 1_500_000 and np.array_equal(valid, v2)
+    assert 0.2 < valid.mean() < 0.95, "the static capture skip should remove a good share of this grid"
+    assert rel_err(sv, dense) <= 1e-11
+    # the static skip rule, restated: capture > region length + max_mip_overlap (and not the smallest size)
+    for i, r in enumerate(regions):
+        g = valid[offs[i]:offs[i + 1]].reshape(-1, len(cfg.captures), cfg.n_pairs, 2)
+        for ci, cap in enumerate(cfg.captures):
+            skipped = cap > r.stop_flanked - r.start_flanked + cfg.max_mip_overlap and cap - cfg.capture_increment >= cfg.min_capture
+            if skipped:
+                assert not g[:, ci].any()
+            else:
+                assert g[5:-5, ci].all()
+    # oracle on a random sample of valid grid points
+    rng = np.random.default_rng(9)
+    picks = np.sort(rng.choice(np.nonzero(valid)[0], 200, replace=False))
+    cands, lrc = [], []
+    for gidx in picks:
+        ri = int(np.searchsorted(offs, gidx, side="right") - 1)
+        r = regions[ri]
+        cands.append(cut_candidate(oracle, r, *decode(cfg, r, int(gidx - offs[ri]))))
+        lrc.append(r.lrc)
+    want_lo = np.array([oracle.get_score(c["ext"], c["lig"], c["tgt"]) for c in cands])
+    assert rel_err(lo[picks], want_lo) <= 1e-12
+    lo2, sv2, _ft = ctx.score_candidates(cands, np.array(lrc), mg.MG_WANT_LOGISTIC | mg.MG_WANT_SVR)
+    assert np.array_equal(lo2, lo[picks]) and rel_err(sv[picks], sv2) <= 1e-11
+    ctx.close()
+
+
+def test_score_only_harness_cfg1():
+    """BASELINE.json configs[0]: 1e5 explicit candidate MIPs (162 bp capture, 16-24 bp arms, consecutive scan
+    starts, both strands) through Featurev5 + logistic + SVR.  Full size on the GPU; the oracle checks a sample."""
+    from oracle_api import Oracle
+    from helpers import random_model
+    oracle = Oracle()
+    rng = np.random.default_rng(1)
+    genome = panel.lcg_genome(60000, 31337)
+    n_pairs = 50000
+    cands = []
+    for i in range(n_pairs):
+        e, l = int(rng.integers(16, 25)), int(rng.integers(16, 25))
+        s = 1000 + i  # consecutive scan starts (0-based offset of the insert)
+        size = 162 - e - l
+        ext, tgt, lig = genome[s - e:s], genome[s:s + size], genome[s + size:s + size + l]
+        cands.append(dict(ext=ext, lig=lig, tgt=tgt, ext_copy=1, lig_copy=1))
+        # the minus-strand MIP over the same insert: arms swap sides and everything is reverse-complemented
+        cands.append(dict(ext=oracle.reverse_comp(genome[s + size:s + size + e]), lig=oracle.reverse_comp(genome[s - l:s]),
+                          tgt=oracle.reverse_comp(tgt), ext_copy=int(rng.choice([1, 2, 3, 10, 100, 101])), lig_copy=1))
+    lrc = np.tile(oracle.long_range_content(genome[:3000], 1001, 2000), (len(cands), 1))
+    ctx = mg.Context(0)
+    model = random_model(oracle, panel.Config(), 256, 3, os.path.join(tmpdir(), "m.model"))
+    ctx.load_svr_model(model)
+    lo, sv, ft = ctx.score_candidates(cands, lrc, mg.MG_WANT_LOGISTIC | mg.MG_WANT_SVR | mg.MG_WANT_FEATURES)
+    assert lo.shape == (100000,) and np.isfinite(sv).all() and ((lo > 0) & (lo < 1)).all()
+    picks = rng.choice(len(cands), 300, replace=False)
+    h = oracle.svm_load_model(model)
+    for k in picks:
+        c = cands[k]
+        wf = oracle.get_parameters(c["ext"], c["lig"], c["tgt"], lrc[k], ext_copy=c["ext_copy"], lig_copy=c["lig_copy"])
+        assert np.array_equal(wf, ft[k])
+        assert rel_err([lo[k]], [oracle.get_score(c["ext"], c["lig"], c["tgt"], ext_copy=c["ext_copy"], lig_copy=c["lig_copy"])]) <= 1e-12
+        assert rel_err([sv[k]], [oracle.svm_predict(h, wf)]) <= 1e-9
+    oracle.svm_free(h)
+    ctx.close()
