@@ -301,30 +301,33 @@ k_svr_fact(const DevFact *__restrict__ fc, const DevFTask *__restrict__ tasks, i
             for (int ui = 0; ui < my_units; ui++) {
                 const int u = unit_list[warp * kUnitsPerWarp + ui];
                 const double *F, *S, *ssb;
-                int ld, ksteps, row0;
+                int ld, row0;
                 bool is_ins = false, is_lig;
                 if (u < uI) {
-                    F = FI + (u * 8) * FACT_LD_INS; ld = FACT_LD_INS; ksteps = FACT_K_INS / 4; S = sb + FACT_OFF_INS;
+                    F = FI + (u * 8) * FACT_LD_INS; ld = FACT_LD_INS; S = sb + FACT_OFF_INS;
                     ssb = sb + FACT_OFF_SS + 2 * C; row0 = RA + RQ + u * 8; is_ins = true; is_lig = false;
                 } else if (u < uI + uQ) {
                     const int m = u - uI;
-                    F = FQ + (m * 8) * FACT_LD_ARM; ld = FACT_LD_ARM; ksteps = FACT_K_ARM / 4; row0 = RA + m * 8; is_lig = ligQ;
+                    F = FQ + (m * 8) * FACT_LD_ARM; ld = FACT_LD_ARM; row0 = RA + m * 8; is_lig = ligQ;
                     S = sb + (is_lig ? FACT_OFF_LIG : FACT_OFF_EXT); ssb = sb + FACT_OFF_SS + (is_lig ? C : 0);
                 } else {
                     const int m = u - uI - uQ;
-                    F = FA + (m * 8) * FACT_LD_ARM; ld = FACT_LD_ARM; ksteps = FACT_K_ARM / 4; row0 = m * 8; is_lig = ligA;
+                    F = FA + (m * 8) * FACT_LD_ARM; ld = FACT_LD_ARM; row0 = m * 8; is_lig = ligA;
                     S = sb + (is_lig ? FACT_OFF_LIG : FACT_OFF_EXT); ssb = sb + FACT_OFF_SS + (is_lig ? C : 0);
                 }
-                // 4 independent accumulator chains: 2 column fragments x even/odd k-steps
+                // 4 independent accumulator chains: 2 column fragments x even/odd k.  One 16-byte load serves two
+                // k4 steps: the lane with thread-in-group t holds columns 8i+2t (even step) and 8i+2t+1 (odd step)
                 double a[2][2] = {{0.0, 0.0}, {0.0, 0.0}}, b[2][2] = {{0.0, 0.0}, {0.0, 0.0}};
-                const double *fa = F + gid * ld + tig, *s0 = S + gid * ld + tig, *s1 = S + (8 + gid) * ld + tig;
-#pragma unroll 2
-                for (int ks = 0; ks < ksteps; ks += 2) {
-                    const double f0 = fa[ks * 4], f1 = fa[ks * 4 + 4];
-                    dmma884(a[0][0], a[0][1], f0, s0[ks * 4]);
-                    dmma884(a[1][0], a[1][1], f0, s1[ks * 4]);
-                    dmma884(b[0][0], b[0][1], f1, s0[ks * 4 + 4]);
-                    dmma884(b[1][0], b[1][1], f1, s1[ks * 4 + 4]);
+                const double2 *fa = reinterpret_cast<const double2 *>(F + gid * ld + 2 * tig);
+                const double2 *s0 = reinterpret_cast<const double2 *>(S + gid * ld + 2 * tig);
+                const double2 *s1 = reinterpret_cast<const double2 *>(S + (8 + gid) * ld + 2 * tig);
+#pragma unroll 3
+                for (int it = 0; it < ld / 8; it++) {
+                    const double2 f = fa[it * 4], p0 = s0[it * 4], p1 = s1[it * 4];
+                    dmma884(a[0][0], a[0][1], f.x, p0.x);
+                    dmma884(a[1][0], a[1][1], f.x, p1.x);
+                    dmma884(b[0][0], b[0][1], f.y, p0.y);
+                    dmma884(b[1][0], b[1][1], f.y, p1.y);
                 }
                 const int row = row0 + gid;
                 const double base = xx[row];

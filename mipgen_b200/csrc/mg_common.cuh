@@ -112,8 +112,8 @@ __host__ __device__ inline uint32_t fd_pack(uint32_t kind, uint32_t part, uint32
 #define FACT_THREADS ((FACT_MATH_WARPS + FACT_GATHER_WARPS + 1) * 32)   // + 1 producer warp
 #define FACT_K_ARM 24      // 21 arm ratios + arm length + log copy, padded to a multiple of 4 (either role)
 #define FACT_K_INS 88      // 86 insert features
-#define FACT_LD_ARM 28     // strides == 12 mod 16 doubles: conflict-free LDS.64 fragment loads
-#define FACT_LD_INS 92
+#define FACT_LD_ARM 24     // strides == 8 mod 16 doubles: conflict-free LDS.128 fragment loads, no padding needed
+#define FACT_LD_INS 88
 #define FACT_OFF_EXT 0
 #define FACT_OFF_LIG (FACT_C * FACT_LD_ARM)
 #define FACT_OFF_INS (FACT_OFF_LIG + FACT_C * FACT_LD_ARM)
