@@ -59,10 +59,12 @@ def fp64_peak_tflops():
     return 37.0, "fallback (nominal B200 FP64 tensor 37 TFLOP/s; no measured file)"
 
 
-def make_panel(cfg: panel.Config, n_regions: int, seed: int):
+def make_panel(cfg: panel.Config, n_regions: int, seed: int, layout_seed: int = None):
+    """Random-sequence genome from `seed`; region lengths/positions from `layout_seed` (default seed+1).
+    Under torchrun every rank uses the same layout (equal work per GPU: weak scaling) on its own genome."""
     glen = panel.genome_length_for(n_regions, LEN_HI, cfg)
     genome = panel.lcg_genome(glen, seed)
-    return genome, panel.make_regions(genome, n_regions, LEN_LO, LEN_HI, cfg, seed + 1)
+    return genome, panel.make_regions(genome, n_regions, LEN_LO, LEN_HI, cfg, seed + 1 if layout_seed is None else layout_seed)
 
 
 # ----------------------------------------------------------------------------------
@@ -224,7 +226,7 @@ def main():
     ctx = mg.Context(local_rank)
     ctx.set_config(cfg)
     model_path = build_model(ctx, cfg, work)
-    genome, regions = make_panel(cfg, N_REGIONS, GENOME_SEED + rank)
+    genome, regions = make_panel(cfg, N_REGIONS, GENOME_SEED + rank, layout_seed=GENOME_SEED + 1)
     for r in regions:
         r.lrc = ctx.long_range_content(r.flank_seq, r.seq_start, r.seq_stop)
 
