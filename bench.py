@@ -164,12 +164,12 @@ def cpu_baseline(cfg, model_path, lrc_by_region, genome, budget_s=12.0, cores=No
 
 
 # ----------------------------------------------------------------------------------
-def build_model(ctx, cfg, work: str):
+def build_model(ctx, cfg, work: str, n_model_regions: int = 4):
     """2048 SVs = feature rows of random candidates from a different genome seed, alpha ~ U(-1,1),
     calibrated so scores straddle 1.5 / 2.2; written and re-read as a libsvm text model."""
     import mipgen_b200 as mg
     rng = np.random.default_rng(MODEL_SEED)
-    genome, regs = make_panel(cfg, 4, MODEL_SEED)
+    genome, regs = make_panel(cfg, n_model_regions, MODEL_SEED)
     for r in regs:
         r.lrc = ctx.long_range_content(r.flank_seq, r.seq_start, r.seq_stop)
     _o, valid, _l, _s, feats = ctx.score_regions(regs, mg.MG_WANT_FEATURES)
@@ -200,6 +200,9 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--workload", default="cfg3", choices=["cfg3", "target1mb"],
+                    help="cfg3 (default): 60-region exon panel per GPU, capture 162.  target1mb: the north star's target run -- "
+                         "4000 regions (~1 Mb), capture sweep 120..250 step 5 (27 sizes), SVR, regions sharded over the ranks")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -207,6 +210,8 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     cfg = panel.Config()  # capture 162/162, 57 default arm pairs
     work = tempfile.mkdtemp(prefix="mipgen_bench_")
+    if args.workload == "target1mb":
+        return target_run(args, rank, local_rank, world, work)
     config = {"workload": "cfg3: %d-region synthetic exon panel per GPU (region length U[%d,%d]), capture 162, 57 arm pairs, "
                           "-score_method svr, %d-SV synthetic RBF model" % (N_REGIONS, LEN_LO, LEN_HI, N_SV),
               "regions_per_gpu": N_REGIONS, "n_sv": N_SV, "sharding": "regions by rank, no collective",
@@ -367,6 +372,88 @@ def main():
         if not args.no_cpu_baseline and world == 1:
             line["cpu_baseline"] = cpu_baseline(cfg, model_path, regions[0].lrc, genome)
         print(json.dumps(line))
+    pnl.close()
+    ctx.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def target_run(args, rank, local_rank, world, work):
+    """North-star target: the FULL candidate grid of a ~1 Mb synthetic target panel (4000 regions of
+    U[150,350] bp, capture 120..250 step 5 = 27 sizes x 57 arm pairs x 2 strands = 6156 grid points per scan
+    start, ~5.6e9 grid points) scored with SVR.  Fixed total work, regions LPT-sharded over the ranks
+    (strong scaling), no collective on the data path."""
+    os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+    import torch
+    import mipgen_b200 as mg
+    from mipgen_b200 import shard
+    if world > 1:
+        import torch.distributed as dist
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    ctx = mg.Context(local_rank)
+    # model: SVs from a trimmed capture sweep so they span the same scan sizes
+    mcfg = panel.Config(250, 120, 65)
+    ctx.set_config(mcfg)
+    build_model(ctx, mcfg, work, n_model_regions=2)
+    cfg = panel.Config(250, 120, 5)
+    ctx.set_config(cfg)
+    n_total = 4000
+    glen = panel.genome_length_for(n_total, 350, cfg)
+    genome = panel.lcg_genome(glen, GENOME_SEED)
+    regions = panel.make_regions(genome, n_total, 150, 350, cfg, GENOME_SEED + 1)
+    target_bp = sum(r.stop_flanked - r.start_flanked + 1 for r in regions)
+    costs = [cfg.grid_size(r) for r in regions]
+    mine = [regions[i] for i in shard.lpt_assign(costs, world)[rank]]
+    for r in mine:
+        r.lrc = ctx.long_range_content(r.flank_seq, r.seq_start, r.seq_stop)
+    pnl = ctx.panel(mine)
+    n_cand = pnl.n_candidates
+
+    def reduce(x, op):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=op)
+        return float(t.item())
+
+    def barrier():
+        ctx.sync()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+
+    steps, warm = max(1, min(args.steps, 3)), max(1, min(args.warmup, 1))
+    for _ in range(warm):
+        pnl.score(mg.MG_WANT_SVR)
+    barrier()
+    ctx.reset_timings()
+    ctx.timer_start()
+    for _ in range(steps):
+        pnl.score(mg.MG_WANT_SVR)
+    ms = ctx.timer_stop()
+    barrier()
+    tm = ctx.timings()
+    n_valid = pnl.valid_candidates()
+    ms = reduce(ms, dist.ReduceOp.MAX if world > 1 else None) / steps
+    total = reduce(float(n_cand), dist.ReduceOp.SUM if world > 1 else None)
+    total_valid = reduce(float(n_valid), dist.ReduceOp.SUM if world > 1 else None)
+    if rank == 0:
+        peak, peak_src = fp64_peak_tflops()
+        issued = tm.svr_dmma * 512.0 + tm.svr_exp * 38.0 + tm.svr_gather * 4.0
+        print(json.dumps({
+            "metric": "candidate MIPs scored/sec (SVR)", "value": total / (ms / 1e3), "unit": "candidates/s", "n_gpus": world,
+            "steps": steps, "warmup": warm, "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "north-star target: full candidate grid of a ~1 Mb synthetic target panel (%d regions, %d target bp), "
+                                   "capture 120..250 step 5, 57 arm pairs, SVR, %d-SV model; regions LPT-sharded over %d rank(s)"
+                                   % (n_total, target_bp, N_SV, world)},
+            "grid_points_per_step": total, "statically_valid_per_step": total_valid,
+            "valid_candidates_per_s": total_valid / (ms / 1e3),
+            "kernel_ms_rank0": {"k_feat": tm.ms_feat / steps, "k_svr": tm.ms_svr / steps},
+            "roofline": {"kernel": "k_svr_fact", "bound": "tensor", "achieved": issued / (tm.ms_svr / 1e3) / 1e12, "peak": peak,
+                         "unit": "TFLOP/s", "frac": issued / (tm.ms_svr / 1e3) / 1e12 / peak, "peak_source": peak_src, "traffic": None},
+        }))
     pnl.close()
     ctx.close()
     if world > 1:

@@ -915,10 +915,7 @@ extern "C" int mg_panel_create(mg_ctx *ctx, const mg_region *regions, int n, mg_
         mg_dev_free(ctx, d_ascii);
         if (rc != MG_OK) { mg_panel_destroy(p); return rc; }
     }
-    if (p->n_cand > 0) {
-        P_TRY(mg_dev_alloc(ctx, (void **)&p->d_valid, (size_t)p->n_cand));
-        P_TRY(mg_dev_alloc(ctx, (void **)&p->d_logistic, (size_t)p->n_cand * 8));
-    }
+    if (p->n_cand > 0) P_TRY(mg_dev_alloc(ctx, (void **)&p->d_valid, (size_t)p->n_cand));
 #undef P_TRY
     *out = p;
     return MG_OK;
@@ -933,6 +930,7 @@ extern "C" int mg_panel_score(mg_ctx *ctx, mg_panel *p, int want)
     if (p->n_cand == 0) return MG_OK;
     CUDA_TRY(ctx, cudaSetDevice(ctx->device));
     const bool w_log = want & MG_WANT_LOGISTIC, w_svr = want & MG_WANT_SVR, w_feat = want & MG_WANT_FEATURES;
+    if (w_log && !p->d_logistic) CUDA_TRY(ctx, mg_dev_alloc(ctx, (void **)&p->d_logistic, (size_t)p->n_cand * 8));
     if (w_svr && !p->d_svr) CUDA_TRY(ctx, mg_dev_alloc(ctx, (void **)&p->d_svr, (size_t)p->n_cand * 8));
     if (w_feat && !p->d_feat) {
         int64_t rows = (p->n_cand + SVR_BM - 1) / SVR_BM * SVR_BM;
