@@ -268,7 +268,7 @@ __device__ __noinline__ double logistic_score(const Stash &s, const double *__re
 constexpr int PF_DI = 64, PF_MONO = 80, PF_GC = 84, PF_NDASH = 85, PF_OTHER = 86, PF_TRANS = 87, PF_ROWS = 88;
 constexpr int kRecipN = 512;
 // per-warp candidate records (field-major, 32 candidates): 11 ints + 2 doubles
-enum { GW_FLAGS = 0, GW_JCODE, GW_EXT_A, GW_EXT_N, GW_EXT_LEN, GW_LIG_A, GW_LIG_N, GW_LIG_LEN, GW_TGT_A, GW_TGT_N, GW_SCAN, GW_PAD,
+enum { GW_FLAGS = 0, GW_JCODE, GW_EXT_A, GW_EXT_N, GW_EXT_LEN, GW_LIG_A, GW_LIG_N, GW_LIG_LEN, GW_TGT_A, GW_TGT_N, GW_SCAN, GW_GOFF,
        GW_LCE = 12, GW_LCL = 14, GW_FIELDS = 16 };
 
 struct WinSmem {
@@ -379,7 +379,6 @@ k_feat_window(const DevConfig *__restrict__ cfg, const DevRegion *__restrict__ r
 #pragma unroll
     for (int m = 0; m < 6; m++) { rowoff_f[m] = (int)((fd[m] >> 7) & 255) * stride; rowoff_r[m] = (int)((fd[m] >> 15) & 255) * stride; }
 
-    const int per_scan = wc.n_cap * wc.n_pairs * 2;
     const int max_arm = cfg->max_arm, min_arm = cfg->min_arm;
 
     for (int ti = task0 + blockIdx.x; ti < task1; ti += gridDim.x) {
@@ -437,6 +436,7 @@ k_feat_window(const DevConfig *__restrict__ cfg, const DevRegion *__restrict__ r
         const double lrc_r0 = lane >= 22 ? lrc_s[lane - 22] : 0.0, lrc_r1 = lrc_s[10 + lane], lrc_r2 = lane < 2 ? lrc_s[42 + lane] : 0.0;
         WinSmem w;
         w.P = P; w.stride = stride; w.codes = codes_s; w.rn = rn; w.lrc = lrc_s; w.span_len = span_len;
+        const int per_scan = tk.nci * wc.n_pairs * 2;  // this work item's grid points per scan start
         const int n_c = tk.nsi * per_scan;
         int *gw = geo_s + warp * (GW_FIELDS * 32);  // this warp's candidate records, field-major
         for (int blk = warp; blk * 32 < n_c; blk += kWarpsPerBlock) {
@@ -444,13 +444,15 @@ k_feat_window(const DevConfig *__restrict__ cfg, const DevRegion *__restrict__ r
             const int j = blk * 32 + lane;
             Geo g;
             g.ok = 0;
-            int flags = 0, jcode = -1;
+            int flags = 0, jcode = -1, goff = 0;
             double lce = 0.0, lcl = 0.0;  // log10(1)
             if (j < n_c) {
                 const int si = j / per_scan;
                 const int rem = j - si * per_scan;
-                const int ci = (rem >> 1) / wc.n_pairs;
-                g = candidate_geometry(wc, r, span0, tk.si0 + si, ci, (rem >> 1) - ci * wc.n_pairs, rem & 1);
+                const int cr = (rem >> 1) / wc.n_pairs, pp = (rem >> 1) - cr * wc.n_pairs, ci = tk.ci0 + cr;
+                // offset of this grid point from the window's first one, in reference enumeration order
+                goff = ((si * wc.n_cap + ci) * wc.n_pairs + pp) * 2 + (rem & 1);
+                g = candidate_geometry(wc, r, span0, tk.si0 + si, ci, pp, rem & 1);
                 int ext_copy = 1, lig_copy = 1;
                 bool invalid = false;
                 if (g.ok) {
@@ -468,7 +470,7 @@ k_feat_window(const DevConfig *__restrict__ cfg, const DevRegion *__restrict__ r
                                       g.scan_size < kRecipN;
                     flags = 1 | (invalid ? 2 : 0) | (fast ? 4 : 0) | (g.rc ? 8 : 0);
                 }
-                if (valid) valid[tk.g0 + j] = (uint8_t)g.ok;
+                if (valid) valid[tk.g0 + goff] = (uint8_t)g.ok;
                 if (logistic) {
                     Stash st;
                     st.state = !g.ok ? 0 : (invalid ? 1 : 2);
@@ -500,14 +502,14 @@ k_feat_window(const DevConfig *__restrict__ cfg, const DevRegion *__restrict__ r
                         st.runs = runs; st.ext_len = g.ext_len; st.lig_len = g.lig_len; st.scan_size = g.scan_size;
                         st.jcode = jcode; st.ext_copy = ext_copy; st.lig_copy = lig_copy;
                     }
-                    logistic[tk.g0 + j] = logistic_score(st, logtab);
+                    logistic[tk.g0 + goff] = logistic_score(st, logtab);
                 }
             }
             if (!x) continue;
 
             // ---- phase 2: the warp writes the 32 feature rows, reading each record by broadcast ----
             __syncwarp();
-            gw[GW_FLAGS * 32 + lane] = flags; gw[GW_JCODE * 32 + lane] = jcode;
+            gw[GW_FLAGS * 32 + lane] = flags; gw[GW_JCODE * 32 + lane] = jcode; gw[GW_GOFF * 32 + lane] = goff;
             gw[GW_EXT_A * 32 + lane] = g.ext_a; gw[GW_EXT_N * 32 + lane] = g.ext_n; gw[GW_EXT_LEN * 32 + lane] = g.ext_len;
             gw[GW_LIG_A * 32 + lane] = g.lig_a; gw[GW_LIG_N * 32 + lane] = g.lig_n; gw[GW_LIG_LEN * 32 + lane] = g.lig_len;
             gw[GW_TGT_A * 32 + lane] = g.tgt_a; gw[GW_TGT_N * 32 + lane] = g.tgt_n; gw[GW_SCAN * 32 + lane] = g.scan_size;
@@ -515,9 +517,10 @@ k_feat_window(const DevConfig *__restrict__ cfg, const DevRegion *__restrict__ r
             reinterpret_cast<double *>(gw + GW_LCL * 32)[lane] = lcl;
             __syncwarp();
             const int jend = min(32, n_c - blk * 32);
-            double *xrow = x + (tk.g0 + (int64_t)blk * 32 - g_base) * MG_NFEAT + lane;
-            for (int c = 0; c < jend; c++, xrow += MG_NFEAT) {
+            double *xbase = x + (tk.g0 - g_base) * MG_NFEAT + lane;
+            for (int c = 0; c < jend; c++) {
                 const int fl = gw[GW_FLAGS * 32 + c];
+                double *xrow = xbase + (int64_t)gw[GW_GOFF * 32 + c] * MG_NFEAT;
                 if (!(fl & 1) || (fl & 2)) {
                     // statically skipped grid point (never read) or invalid candidate: 192 zeros
 #pragma unroll

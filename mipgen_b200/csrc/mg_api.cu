@@ -847,18 +847,29 @@ extern "C" int mg_panel_create(mg_ctx *ctx, const mg_region *regions, int n, mg_
         W = W / 8 * 8;  // factored-SVR windows (8, 4, 2 or 1 scan starts) must nest inside K-feat windows
         const int64_t per_scan = (int64_t)ctx->cfg.n_cap * (int64_t)ctx->cfg.ext_len.size() * 2;
         while (W > 1 && W * per_scan > (1 << 24)) W /= 2;  // keep a window's candidate count in int range
+        const int n_cap = ctx->cfg.n_cap, n_pairs2 = (int)ctx->cfg.ext_len.size() * 2;
+        // captures per K-feat work item: keep a work item around 8-16 k candidates
+        const int nci_max = std::max(1, std::min(n_cap, 16384 / std::max(1, W * n_pairs2)));
         for (int i = 0; i < n; i++)
             for (int si = 0; si < p->h_regions[i].n_scan; si += W) {
                 DevTask t;
                 t.region = i; t.si0 = si; t.nsi = std::min(W, p->h_regions[i].n_scan - si); t.pad = 0;
+                t.ci0 = 0; t.nci = n_cap;
                 t.g0 = p->h_regions[i].grid_off + (int64_t)si * per_scan;
-                p->h_tasks.push_back(t);
+                p->task_start.push_back((int)p->h_tasks.size());
+                p->h_windows.push_back(t);
+                for (int c0 = 0; c0 < n_cap; c0 += nci_max) {
+                    DevTask u = t;
+                    u.ci0 = c0; u.nci = std::min(nci_max, n_cap - c0);
+                    p->h_tasks.push_back(u);
+                }
             }
-        // factored-SVR tasks, grouped by K-feat window so a chunk of windows is a contiguous task range
-        p->ftask_start.assign(p->h_tasks.size() + 1, 0);
+        p->task_start.push_back((int)p->h_tasks.size());
+        // factored-SVR tasks, grouped by window so a chunk of windows is a contiguous task range
+        p->ftask_start.assign(p->h_windows.size() + 1, 0);
         if (ctx->fact_ok && W % ctx->fact_W == 0) {
-            for (size_t k = 0; k < p->h_tasks.size(); k++) {
-                const DevTask &t = p->h_tasks[k];
+            for (size_t k = 0; k < p->h_windows.size(); k++) {
+                const DevTask &t = p->h_windows[k];
                 p->ftask_start[k] = (int)p->h_ftasks.size();
                 for (int si = 0; si < t.nsi; si += ctx->fact_W)
                     for (int ci = 0; ci < ctx->cfg.n_cap; ci++)
@@ -870,7 +881,7 @@ extern "C" int mg_panel_create(mg_ctx *ctx, const mg_region *regions, int n, mg_
                             p->h_ftasks.push_back(f);
                         }
             }
-            p->ftask_start[p->h_tasks.size()] = (int)p->h_ftasks.size();
+            p->ftask_start[p->h_windows.size()] = (int)p->h_ftasks.size();
         }
         p->span_cap = W + ctx->cfg.max_arm + ctx->cfg.max_capture - ctx->cfg.min_arm + 4;
         int words = (p->span_cap + 2) / 2;
@@ -938,7 +949,7 @@ extern "C" int mg_panel_score(mg_ctx *ctx, mg_panel *p, int want)
         CUDA_TRY(ctx, cudaMemsetAsync(p->d_feat, 0, (size_t)rows * MG_NFEAT * 8, ctx->stream));
     }
     int rc = MG_OK;
-    const int n_tasks = (int)p->h_tasks.size();
+    const int n_win = (int)p->h_windows.size(), n_tasks = (int)p->h_tasks.size();
     // factored SVR when the configuration fits its tables (mode 0/2); dense otherwise (mode 1, or as fallback)
     const bool fact = w_svr && ctx->svr_mode != 1 && ctx->fact_ok && !p->h_ftasks.empty();
     if (w_svr && ctx->svr_mode == 2 && !fact) {
@@ -954,30 +965,31 @@ extern "C" int mg_panel_score(mg_ctx *ctx, mg_panel *p, int want)
         }
         if ((rc = launch_lrc_weights(ctx, p, p->d_w)) != MG_OK) return rc;
     }
-    auto svr_range = [&](int t0, int t1, const double *xbuf, int64_t g0, int64_t g1) {
-        if (fact) return launch_svr_fact(ctx, p, p->ftask_start[t0], p->ftask_start[t1], xbuf, g0, g1 - g0, p->d_valid, p->d_w, p->d_svr);
+    // windows [w0, w1) <-> candidates [g0, g1)
+    auto svr_range = [&](int w0, int w1, const double *xbuf, int64_t g0, int64_t g1) {
+        if (fact) return launch_svr_fact(ctx, p, p->ftask_start[w0], p->ftask_start[w1], xbuf, g0, g1 - g0, p->d_valid, p->d_w, p->d_svr);
         return launch_svr(ctx, xbuf, g1 - g0, p->d_valid + g0, p->d_svr + g0);
     };
     if (!w_svr && !w_feat) {
         rc = launch_feat_grid(ctx, p, 0, n_tasks, 0, p->n_cand, p->d_valid, w_log ? p->d_logistic : nullptr, nullptr);
     } else if (w_feat) {
         rc = launch_feat_grid(ctx, p, 0, n_tasks, 0, p->n_cand, p->d_valid, w_log ? p->d_logistic : nullptr, p->d_feat);
-        if (rc == MG_OK && w_svr) rc = svr_range(0, n_tasks, p->d_feat, 0, p->n_cand);
+        if (rc == MG_OK && w_svr) rc = svr_range(0, n_win, p->d_feat, 0, p->n_cand);
     } else {
         // feature rows live only in a workspace: walk the panel in chunks of whole windows
         const int64_t n_chunks = (p->n_cand + kMaxChunkRows - 1) / kMaxChunkRows;
         const int64_t target = std::min<int64_t>(kMaxChunkRows, p->n_cand / n_chunks + (1 << 16));  // even chunks, no tiny tail
-        int t0 = 0;
-        while (t0 < n_tasks && rc == MG_OK) {
-            const int64_t g0 = p->h_tasks[t0].g0;
-            int t1 = t0 + 1;
-            auto end_of = [&](int t) { return t < n_tasks ? p->h_tasks[t].g0 : p->n_cand; };
-            while (t1 < n_tasks && end_of(t1 + 1) - g0 <= target) t1++;
-            const int64_t g1 = end_of(t1);
+        int w0 = 0;
+        while (w0 < n_win && rc == MG_OK) {
+            const int64_t g0 = p->h_windows[w0].g0;
+            int w1 = w0 + 1;
+            auto end_of = [&](int w) { return w < n_win ? p->h_windows[w].g0 : p->n_cand; };
+            while (w1 < n_win && end_of(w1 + 1) - g0 <= target) w1++;
+            const int64_t g1 = end_of(w1);
             if ((rc = ensure_x(ctx, g1 - g0)) != MG_OK) return rc;
-            rc = launch_feat_grid(ctx, p, t0, t1, g0, g1 - g0, p->d_valid, w_log ? p->d_logistic : nullptr, ctx->d_x);
-            if (rc == MG_OK) rc = svr_range(t0, t1, ctx->d_x, g0, g1);
-            t0 = t1;
+            rc = launch_feat_grid(ctx, p, p->task_start[w0], p->task_start[w1], g0, g1 - g0, p->d_valid, w_log ? p->d_logistic : nullptr, ctx->d_x);
+            if (rc == MG_OK) rc = svr_range(w0, w1, ctx->d_x, g0, g1);
+            w0 = w1;
         }
     }
     if (rc == MG_OK) {

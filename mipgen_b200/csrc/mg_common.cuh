@@ -40,11 +40,13 @@ struct DevRegion {
     int pad;
 };
 
-// one K-feat work item: a window of consecutive scan starts of one region
+// one K-feat work item: a window of consecutive scan starts of one region, restricted to a range of
+// capture sizes (so that a capture sweep does not blow a work item up to 1e5+ candidates)
 struct DevTask {
-    int64_t g0;      // global candidate index of the window's first grid point
+    int64_t g0;      // global candidate index of the window's first grid point (capture index 0)
     int region;      // index into DevRegion[]
     int si0, nsi;    // first scan index of the window, number of scan starts
+    int ci0, nci;    // capture-size indices [ci0, ci0 + nci)
     int pad;
 };
 
@@ -203,10 +205,12 @@ struct mg_panel {
     std::vector<int64_t> offsets;  // n+1
     std::vector<DevRegion> h_regions;
     DevRegion *d_regions = nullptr;
-    std::vector<DevTask> h_tasks;  // K-feat windows, ascending in g0
+    std::vector<DevTask> h_windows;  // scan-start windows (all capture sizes), ascending in g0: the unit of chunking
+    std::vector<DevTask> h_tasks;    // K-feat work items: windows split along the capture dimension
+    std::vector<int> task_start;     // [n_windows+1] first K-feat work item of each window
     DevTask *d_tasks = nullptr;
     std::vector<DevFTask> h_ftasks;     // factored-SVR tasks, grouped by K-feat window
-    std::vector<int> ftask_start;       // [n_tasks+1] first factored task of each K-feat window
+    std::vector<int> ftask_start;       // [n_windows+1] first factored task of each window
     DevFTask *d_ftasks = nullptr;
     double *d_w = nullptr;              // [n_regions][n_sv_pad] alpha * exp(-g d_lrc)
     int w_n_sv_pad = 0;
