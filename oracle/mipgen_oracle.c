@@ -628,3 +628,97 @@ long orc_tile_replay(const orc_region *r, const orc_cfg *c, const unsigned char 
     }
     return n;
 }
+
+/* ------------------------------------------------------------------------- */
+/* selection front-end                                                        */
+/* ------------------------------------------------------------------------- */
+
+typedef struct { int si, ci, p, strand, s, cap, e, l, scan_stop, ext_copy, lig_copy; } orc_dec;
+
+static void decode_idx(const orc_region *r, const orc_cfg *c, long idx, orc_dec *d)
+{
+    int inc = c->capture_increment == 0 ? 1 : c->capture_increment;
+    int ncap = orc_n_captures(c);
+    d->strand = (int)(idx & 1);
+    long q = idx >> 1;
+    d->p = (int)(q % c->n_pairs); q /= c->n_pairs;
+    d->ci = (int)(q % ncap);
+    d->si = (int)(q / ncap);
+    d->s = orc_first_scan_start(r, c) + d->si;
+    d->cap = c->max_capture - d->ci * inc;
+    d->e = c->ext_len[d->p]; d->l = c->lig_len[d->p];
+    d->scan_stop = d->s + d->cap - (d->e + d->l) - 1;
+    orc_geom g;
+    orc_geometry(d->s, d->scan_stop, d->e, d->l, d->strand, &g);
+    d->ext_copy = copy_lookup(r, c, g.ext_start, g.ext_stop);
+    d->lig_copy = copy_lookup(r, c, g.lig_start, g.lig_stop);
+}
+
+int orc_n_positions(const orc_region *r, const orc_cfg *c)
+{
+    int last = r->stop_flanked + c->max_capture - min_sum(c) - 1;
+    int n = last - orc_first_scan_start(r, c) + 1;
+    return n < 0 ? 0 : n;
+}
+
+void orc_condense(const orc_region *r, const orc_cfg *c, const orc_sel *sel, const double *score,
+                  const long *enum_idx, long n_enum, long *scan_best)
+{
+    /* mipgen.cpp:1670-1746 with arm_fraction_masked = 0, snp_count = 0, mapping_failed = '0' */
+    int nscan = orc_n_scan(r, c);
+    for (long i = 0; i < 2L * nscan; i++) scan_best[i] = -1;
+    /* the candidates of one scan start are contiguous in enum_idx; walk each block backwards per strand */
+    long b = 0;
+    while (b < n_enum) {
+        orc_dec d0; decode_idx(r, c, enum_idx[b], &d0);
+        long e = b;
+        while (e < n_enum) { orc_dec d; decode_idx(r, c, enum_idx[e], &d); if (d.si != d0.si) break; e++; }
+        int chosen_copy_count = 0;
+        for (int strand = 0; strand < 2; strand++) {
+            int skip_ahead = 0;
+            long best = -1;
+            for (long k = e - 1; k >= b; k--) {
+                if (skip_ahead) continue;
+                orc_dec d; decode_idx(r, c, enum_idx[k], &d);
+                if (d.strand != strand) continue;
+                if (d.ext_copy * d.lig_copy > sel->max_arm_copy) continue;                 /* :1689 */
+                int current = d.ext_copy > d.lig_copy ? d.ext_copy : d.lig_copy;          /* :1692 */
+                double sc = score[enum_idx[k]];
+                if (best < 0) { best = enum_idx[k]; chosen_copy_count = current; }         /* :1695-1700 */
+                else if (current > sel->target_arm_copy && current < chosen_copy_count) {  /* :1709 */
+                    best = enum_idx[k]; chosen_copy_count = current;
+                } else if (current <= sel->target_arm_copy) {                              /* :1715 */
+                    if (sc < sel->lower_score_limit && sc > score[best]) { best = enum_idx[k]; chosen_copy_count = current; }
+                    else if (sc > sel->lower_score_limit) {
+                        if (sc > score[best]) {                                            /* :1731-1737 (snp counts equal) */
+                            best = enum_idx[k];
+                            if (sc > sel->upper_score_limit) skip_ahead = 1;
+                        }
+                    }
+                }
+            }
+            scan_best[2L * d0.si + strand] = best;
+        }
+        b = e;
+    }
+}
+
+void orc_collapse(const orc_region *r, const orc_cfg *c, const orc_sel *sel, const double *score,
+                  const long *scan_best, long *pos_best)
+{
+    /* mipgen.cpp:1617-1649 */
+    int nscan = orc_n_scan(r, c), npos = orc_n_positions(r, c), s0 = orc_first_scan_start(r, c);
+    for (long i = 0; i < 2L * npos; i++) pos_best[i] = -1;
+    for (int si = 0; si < nscan; si++)
+        for (int strand = 0; strand < 2; strand++) {
+            long cur = scan_best[2L * si + strand];
+            if (cur < 0) continue;
+            orc_dec d; decode_idx(r, c, cur, &d);
+            if (d.ext_copy * d.lig_copy > sel->max_arm_copy || d.ext_copy > sel->target_arm_copy || d.lig_copy > sel->target_arm_copy) continue;
+            for (int pos = d.s; pos <= d.scan_stop; pos++) {
+                long *slot = &pos_best[2L * (pos - s0) + strand];
+                if (*slot < 0) *slot = cur;
+                else if (score[cur] > score[*slot]) *slot = cur;
+            }
+        }
+}

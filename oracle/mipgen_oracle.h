@@ -116,6 +116,29 @@ long orc_tile_replay(const orc_region *r, const orc_cfg *c, const unsigned char 
                      const double *score, int method, int heuristic, double upper_score_limit,
                      long *out_idx, long cap);
 
+/* ---- selection front-end: best MIP per scan start / per position ---------- */
+/* The knobs of condense_mips / collapse_mips (mipgen.cpp:197-198, 264-265, 177).  Masking (TRF) and SNP
+ * inputs are not modelled: arm_fraction_masked = 0 and snp_count = 0, as in every run without -trf and
+ * -snp_file (the defaults), and mapping_failed = '0' (stub bwa / unique capture sites). */
+typedef struct {
+    double lower_score_limit, upper_score_limit;
+    int max_arm_copy, target_arm_copy;
+} orc_sel;
+
+/* Positions the region's candidates can cover: [orc_first_scan_start, stop_flanked + max_capture - min_sum - 1] */
+int orc_n_positions(const orc_region *r, const orc_cfg *c);
+
+/* condense_mips (mipgen.cpp:1670-1746) over the enumerated candidates (grid indices in enumeration
+ * order, e.g. from orc_tile_replay): scan_best[scan_idx*2 + strand] = grid index of scan_strand_best_mip
+ * or -1.  Lists are walked in push_front order (reverse enumeration, mipgen.cpp:475,489). */
+void orc_condense(const orc_region *r, const orc_cfg *c, const orc_sel *s, const double *score,
+                  const long *enum_idx, long n_enum, long *scan_best);
+
+/* collapse_mips (mipgen.cpp:1617-1649): pos_best[pos_idx*2 + strand] = grid index of pos_strand_best_mip
+ * or -1, pos_idx = position - orc_first_scan_start. */
+void orc_collapse(const orc_region *r, const orc_cfg *c, const orc_sel *s, const double *score,
+                  const long *scan_best, long *pos_best);
+
 #ifdef __cplusplus
 }
 #endif

@@ -43,6 +43,11 @@ class CRegion(C.Structure):
                 ("copies", c_int_p)]
 
 
+class CSel(C.Structure):
+    _fields_ = [("lower_score_limit", C.c_double), ("upper_score_limit", C.c_double), ("max_arm_copy", C.c_int),
+                ("target_arm_copy", C.c_int)]
+
+
 class CCfg(C.Structure):
     _fields_ = [("max_capture", C.c_int), ("min_capture", C.c_int), ("capture_increment", C.c_int),
                 ("max_mip_overlap", C.c_int), ("n_pairs", C.c_int), ("ext_len", c_int_p),
@@ -121,6 +126,12 @@ class _Lib:
             L.orc_tile_replay.restype = C.c_long
             L.orc_tile_replay.argtypes = [C.POINTER(CRegion), C.POINTER(CCfg), c_ubyte_p, c_double_p,
                                           C.c_int, C.c_int, C.c_double, c_long_p, C.c_long]
+            L.orc_n_positions.restype = C.c_int
+            L.orc_n_positions.argtypes = [C.POINTER(CRegion), C.POINTER(CCfg)]
+            L.orc_condense.restype = None
+            L.orc_condense.argtypes = [C.POINTER(CRegion), C.POINTER(CCfg), C.POINTER(CSel), c_double_p, c_long_p, C.c_long, c_long_p]
+            L.orc_collapse.restype = None
+            L.orc_collapse.argtypes = [C.POINTER(CRegion), C.POINTER(CCfg), C.POINTER(CSel), c_double_p, c_long_p, c_long_p]
             L.orc_reverse_comp.restype = None
             L.orc_reverse_comp.argtypes = [C.c_char_p, C.c_int, C.c_char_p]
         else:
@@ -210,6 +221,25 @@ class Oracle(_Lib):
         n = self.lib.orc_tile_replay(C.byref(cr), C.byref(cc), _np_ptr(valid, c_ubyte_p), _np_ptr(score, c_double_p),
                                      method, int(heuristic), upper, out.ctypes.data_as(c_long_p), out.size)
         return out[:n]
+
+
+    def select(self, r: Region, cfg: Config, score: np.ndarray, enum_idx: np.ndarray, lower: float, upper: float,
+               max_arm_copy: int = 75, target_arm_copy: int = 20):
+        """condense_mips + collapse_mips: (scan_best[n_scan,2], pos_best[n_pos,2]) as grid indices (-1: none)."""
+        keep = _Keep()
+        cr, cc = c_region(r, keep), c_cfg(cfg, keep)
+        sel = CSel(lower, upper, max_arm_copy, target_arm_copy)
+        score = np.ascontiguousarray(score, dtype=np.float64)
+        enum_idx = np.ascontiguousarray(enum_idx, dtype=np.int64)
+        n_scan = cfg.n_scan(r)
+        n_pos = self.lib.orc_n_positions(C.byref(cr), C.byref(cc))
+        sb = np.empty((n_scan, 2), dtype=np.int64)
+        pb = np.empty((n_pos, 2), dtype=np.int64)
+        self.lib.orc_condense(C.byref(cr), C.byref(cc), C.byref(sel), _np_ptr(score, c_double_p),
+                              enum_idx.ctypes.data_as(c_long_p), enum_idx.size, sb.ctypes.data_as(c_long_p))
+        self.lib.orc_collapse(C.byref(cr), C.byref(cc), C.byref(sel), _np_ptr(score, c_double_p), sb.ctypes.data_as(c_long_p),
+                              pb.ctypes.data_as(c_long_p))
+        return sb, pb
 
 
 def have_ref() -> bool:
