@@ -178,6 +178,28 @@ int mg_panel_fetch(mg_ctx *ctx, mg_panel *p, uint8_t *valid, double *logistic, d
 /* Raw device pointers of the result arrays (NULL if never computed). */
 int mg_panel_device_ptrs(const mg_panel *p, const uint8_t **valid, const double **logistic, const double **svr);
 
+/* ---- selection front-end on the device ----------------------------- */
+/* condense_mips (mipgen.cpp:1670-1746, on top of the tile loop's score-dependent enumeration,
+ * mipgen.cpp:426-497) and collapse_mips (mipgen.cpp:1617-1649) over a scored panel: the best candidate
+ * per (scan start, strand) and per (position, strand), as global grid indices of the panel (-1: none).
+ * Without TRF masking, SNP data and mapping failures (the defaults); arm copies from the copy tables. */
+typedef struct {
+    int method;                 /* 0 logistic, 1 svr, 2 mixed (tile phase = logistic scores)              */
+    int heuristic;              /* -logistic_heuristic != "off"                                          */
+    double lower_score_limit;   /* -{svr,logistic}_priority_score                                        */
+    double upper_score_limit;   /* -{svr,logistic}_optimal_score                                         */
+    int max_arm_copy;           /* -max_arm_copy_product (75)                                            */
+    int target_arm_copy;        /* -target_arm_copy (20)                                                 */
+} mg_select_params;
+/* number of scan starts / coverable positions of a region (positions: first scan start ..
+ * stop_flanked + max_capture - min arm sum - 1) */
+int mg_region_scan_count(const mg_ctx *ctx, const mg_region *r);
+int mg_region_position_count(const mg_ctx *ctx, const mg_region *r);
+/* scan_best[(scan_offset(region) + scan_idx)*2 + strand], pos_best[(pos_offset(region) + pos_idx)*2 + strand];
+ * offsets are prefix sums of the two counts over the panel's regions.  The panel must have been scored
+ * with the method's scores (MG_WANT_SVR for method 1, MG_WANT_LOGISTIC otherwise). */
+int mg_panel_select(mg_ctx *ctx, mg_panel *p, const mg_select_params *sp, int64_t *scan_best, int64_t *pos_best);
+
 /* ---- host helper: replay of the score-dependent control flow ---------------------- */
 /* Walks one scored region grid exactly like the tile loop (mipgen.cpp:426-497) and
  * writes the grid indices the reference would have enumerated.  method: 0 logistic,

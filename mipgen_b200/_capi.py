@@ -42,6 +42,11 @@ class MgCandidate(C.Structure):
                 ("scan_size", C.c_int), ("ext_copy", C.c_int), ("lig_copy", C.c_int)]
 
 
+class MgSelectParams(C.Structure):
+    _fields_ = [("method", C.c_int), ("heuristic", C.c_int), ("lower_score_limit", C.c_double),
+                ("upper_score_limit", C.c_double), ("max_arm_copy", C.c_int), ("target_arm_copy", C.c_int)]
+
+
 class MgTimings(C.Structure):
     _fields_ = [("ms_feat", C.c_double), ("launches_feat", C.c_long), ("ms_svr", C.c_double),
                 ("launches_svr", C.c_long), ("ms_other", C.c_double), ("launches_other", C.c_long),
@@ -84,6 +89,9 @@ SYMBOLS = [
     ("mg_panel_score", C.c_int, [C.c_void_p, C.c_void_p, C.c_int]),
     ("mg_panel_fetch", C.c_int, [C.c_void_p, C.c_void_p, c_ubyte_p, c_double_p, c_double_p, c_double_p]),
     ("mg_panel_device_ptrs", C.c_int, [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(C.c_void_p)]),
+    ("mg_region_scan_count", C.c_int, [C.c_void_p, C.POINTER(MgRegion)]),
+    ("mg_region_position_count", C.c_int, [C.c_void_p, C.POINTER(MgRegion)]),
+    ("mg_panel_select", C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(MgSelectParams), c_int64_p, c_int64_p]),
     ("mg_tile_replay", C.c_int64, [C.POINTER(MgConfig), C.POINTER(MgRegion), c_ubyte_p, c_double_p, C.c_int, C.c_int,
                                    C.c_double, c_int64_p, C.c_int64]),
 ]
@@ -189,6 +197,23 @@ class Panel:
     def fetch_into(self, valid: Optional[np.ndarray], logistic: Optional[np.ndarray], svr: Optional[np.ndarray]) -> None:
         self.ctx._check(self.ctx.lib.mg_panel_fetch(self.ctx.h, self.h, _ptr(valid, c_ubyte_p), _ptr(logistic, c_double_p),
                                                     _ptr(svr, c_double_p), c_double_p()))
+
+    def select(self, regions: Sequence[Region], method: int, lower: float, upper: float, heuristic: bool = True,
+               max_arm_copy: int = 75, target_arm_copy: int = 20):
+        """condense_mips + collapse_mips on the device.  Returns (scan_offsets, scan_best[n,2], pos_offsets,
+        pos_best[m,2]); entries are global grid indices of the panel or -1."""
+        arr, _keep = _c_regions(regions)
+        n = len(regions)
+        so = np.zeros(n + 1, np.int64)
+        po = np.zeros(n + 1, np.int64)
+        for i in range(n):
+            so[i + 1] = so[i] + self.ctx.lib.mg_region_scan_count(self.ctx.h, C.byref(arr[i]))
+            po[i + 1] = po[i] + self.ctx.lib.mg_region_position_count(self.ctx.h, C.byref(arr[i]))
+        sb = np.empty((int(so[-1]), 2), np.int64)
+        pb = np.empty((int(po[-1]), 2), np.int64)
+        sp = MgSelectParams(method, int(heuristic), lower, upper, max_arm_copy, target_arm_copy)
+        self.ctx._check(self.ctx.lib.mg_panel_select(self.ctx.h, self.h, C.byref(sp), _ptr(sb, c_int64_p), _ptr(pb, c_int64_p)))
+        return so, sb, po, pb
 
     def close(self) -> None:
         if self.h:

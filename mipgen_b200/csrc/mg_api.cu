@@ -1060,6 +1060,55 @@ extern "C" int mg_score_regions(mg_ctx *ctx, const mg_region *regions, int n, in
 }
 
 // ---------------------------------------------------------------------------
+// selection front-end
+// ---------------------------------------------------------------------------
+extern "C" int mg_region_scan_count(const mg_ctx *ctx, const mg_region *r) { return (ctx && ctx->has_cfg && r) ? n_scan(ctx->cfg, r) : 0; }
+
+static int n_positions(const HostConfig &c, const mg_region *r)
+{
+    int n = r->stop_flanked + c.max_capture - c.min_sum - 1 - first_scan_start(c, r) + 1;
+    return n < 0 ? 0 : n;
+}
+
+extern "C" int mg_region_position_count(const mg_ctx *ctx, const mg_region *r) { return (ctx && ctx->has_cfg && r) ? n_positions(ctx->cfg, r) : 0; }
+
+extern "C" int mg_panel_select(mg_ctx *ctx, mg_panel *p, const mg_select_params *sp, int64_t *scan_best, int64_t *pos_best)
+{
+    if (!ctx || !p || p->ctx != ctx || !sp || !scan_best || !pos_best) return MG_ERR_INVALID;
+    const double *d_score = sp->method == 1 ? (p->has_svr ? p->d_svr : nullptr) : (p->has_logistic ? p->d_logistic : nullptr);
+    if (!d_score) { ctx->err = "mg_panel_select: the panel has not been scored with the scores this method selects on"; return MG_ERR_INVALID; }
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    const int n = p->n_regions;
+    std::vector<int64_t> so(n + 1, 0), po(n + 1, 0);
+    for (int i = 0; i < n; i++) {
+        so[i + 1] = so[i] + p->h_regions[i].n_scan;
+        int np = p->h_regions[i].stop_flanked + ctx->cfg.max_capture - ctx->cfg.min_sum - 1 - p->h_regions[i].first_scan + 1;
+        po[i + 1] = po[i] + (np < 0 ? 0 : np);
+    }
+    int64_t *d_so = nullptr, *d_po = nullptr, *d_sb = nullptr, *d_pb = nullptr;
+    auto cleanup = [&]() { mg_dev_free(ctx, d_so); mg_dev_free(ctx, d_po); mg_dev_free(ctx, d_sb); mg_dev_free(ctx, d_pb); };
+#define S_TRY(expr) do { cudaError_t _e = (expr); if (_e != cudaSuccess) { ctx->err = std::string(#expr) + ": " + cudaGetErrorString(_e); cleanup(); return MG_ERR_CUDA; } } while (0)
+    S_TRY(mg_dev_alloc(ctx, (void **)&d_so, (size_t)(n + 1) * 8));
+    S_TRY(mg_dev_alloc(ctx, (void **)&d_po, (size_t)(n + 1) * 8));
+    S_TRY(mg_dev_alloc(ctx, (void **)&d_sb, (size_t)std::max<int64_t>(so[n], 1) * 16));
+    S_TRY(mg_dev_alloc(ctx, (void **)&d_pb, (size_t)std::max<int64_t>(po[n], 1) * 16));
+    S_TRY(cudaMemcpyAsync(d_so, so.data(), (size_t)(n + 1) * 8, cudaMemcpyHostToDevice, ctx->stream));
+    S_TRY(cudaMemcpyAsync(d_po, po.data(), (size_t)(n + 1) * 8, cudaMemcpyHostToDevice, ctx->stream));
+    int rc = launch_select(ctx, p, d_so, d_po, so[n], po[n], d_score, sp->method, sp->heuristic, sp->lower_score_limit,
+                           sp->upper_score_limit, sp->max_arm_copy, sp->target_arm_copy, d_sb, d_pb);
+    if (rc == MG_OK) {
+        S_TRY(cudaMemcpyAsync(scan_best, d_sb, (size_t)so[n] * 16, cudaMemcpyDeviceToHost, ctx->stream));
+        S_TRY(cudaMemcpyAsync(pos_best, d_pb, (size_t)po[n] * 16, cudaMemcpyDeviceToHost, ctx->stream));
+        S_TRY(cudaStreamSynchronize(ctx->stream));  // so/po staging vectors go out of scope
+    } else {
+        cudaStreamSynchronize(ctx->stream);
+    }
+#undef S_TRY
+    cleanup();
+    return rc;
+}
+
+// ---------------------------------------------------------------------------
 // host helper: the score-dependent control flow of the tile loop
 // ---------------------------------------------------------------------------
 extern "C" int64_t mg_tile_replay(const mg_config *cfg, const mg_region *r, const uint8_t *valid, const double *score, int method,

@@ -260,6 +260,9 @@ int launch_feat_explicit(mg_ctx *ctx, const DevCand *d_cands, const uint8_t *d_c
 int launch_svr(mg_ctx *ctx, const double *d_x, int64_t n, const uint8_t *d_valid, double *d_out);
 int launch_svr_setup(mg_ctx *ctx);
 int launch_fact_setup(mg_ctx *ctx);
+int launch_select(mg_ctx *ctx, const mg_panel *p, const int64_t *d_scan_off, const int64_t *d_pos_off, int64_t total_scan,
+                  int64_t total_pos, const double *d_score, int method, int heuristic, double lower, double upper, int max_arm_copy,
+                  int target_arm_copy, int64_t *d_scan_best, int64_t *d_pos_best);
 int launch_lrc_weights(mg_ctx *ctx, const mg_panel *p, double *d_w);
 int launch_svr_fact(mg_ctx *ctx, const mg_panel *p, int ftask0, int ftask1, const double *d_x, int64_t g_base, int64_t n_cand,
                     const uint8_t *d_valid, const double *d_w, double *d_out);
