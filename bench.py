@@ -280,6 +280,15 @@ def main():
     value = total_cand / (ms_per_step / 1e3)
     launches = int(tm.launches_feat + tm.launches_svr + tm.launches_other)
 
+    # ---- selection front-end on the device (condense_mips + collapse_mips over the SVR grid) ----
+    pnl.select(regions, 1, 1.5, 2.2)
+    barrier()
+    ctx.timer_start()
+    for _ in range(args.steps):
+        pnl.select(regions, 1, 1.5, 2.2)
+    ms_select = reduce_max(ctx.timer_stop()) / args.steps
+    barrier()
+
     # ---- logistic, inputs resident ----
     for _ in range(args.warmup):
         pnl.score(mg.MG_WANT_LOGISTIC)
@@ -347,6 +356,8 @@ def main():
             "logistic": {"value": total_cand / (ms_log / 1e3), "unit": "candidates/s", "ms_per_step": ms_log},
             "e2e": {"value": total_cand / (e2e_ms / 1e3), "unit": "candidates/s", "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms, "api": "mg_score_regions (host buffers, pinned outputs)"},
+            "select": {"what": "condense_mips + collapse_mips on the device (mg_panel_select: best MIP per scan start and per "
+                               "position, incl. D2H of the winners)", "ms_per_step": ms_select},
             "gpu_launches": launches,
             "kernel_ms_per_step": {"k_feat": tm.ms_feat / args.steps, "k_svr": tm.ms_svr / args.steps, "other": tm.ms_other / args.steps},
             "roofline": {"kernel": "k_svr_fact" if factored else "k_svr_dmma", "bound": "tensor", "achieved": achieved, "peak": peak,
