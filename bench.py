@@ -164,6 +164,18 @@ def cpu_baseline(cfg, model_path, lrc_by_region, genome, budget_s=12.0, cores=No
 
 
 # ----------------------------------------------------------------------------------
+# FP64-pipe slots per exp epilogue element, counted as FMA = 2 flop each (DMMA and DFMA share one pipe on B200):
+# dense kernel 19 instructions (norm combine, clamp, scale, 11-instruction exp, alpha FMA); factored kernel 12
+# (accumulator start value, even/odd chain add, 10-instruction exp; its tables are pre-scaled by -gamma)
+EXP_FLOP_DENSE, EXP_FLOP_FACT = 38.0, 24.0
+
+
+def issued_fp64_flop(tm) -> float:
+    """FP64 work the K-svr launches really issued: 512 flop per DMMA.8x8x4, the exp epilogue, 2 FMA per gathered triple."""
+    exp_flop = EXP_FLOP_FACT if tm.svr_gather > 0 else EXP_FLOP_DENSE
+    return tm.svr_dmma * 512.0 + tm.svr_exp * exp_flop + tm.svr_gather * 4.0
+
+
 def build_model(ctx, cfg, work: str, n_model_regions: int = 4):
     """2048 SVs = feature rows of random candidates from a different genome seed, alpha ~ U(-1,1),
     calibrated so scores straddle 1.5 / 2.2; written and re-read as a libsvm text model."""
@@ -339,11 +351,9 @@ def main():
         svr_ms_per_launch = tm.ms_svr / max(tm.launches_svr, 1)
         cand_per_launch = tm.candidates_svr / max(tm.launches_svr, 1)
         dense_equiv = cand_per_launch * FLOP_PER_CAND_PER_SV * N_SV / (svr_ms_per_launch / 1e3) / 1e12
-        # FP64 work the launches really issued (DMMA and DFMA share one pipe on B200): 512 flop per DMMA,
-        # ~19 FP64 instructions (counted as FMA = 2 flop) per exp epilogue element, 2 FMA per gathered triple
-        issued_flop = tm.svr_dmma * 512.0 + tm.svr_exp * 38.0 + tm.svr_gather * 4.0
-        achieved = issued_flop / (tm.ms_svr / 1e3) / 1e12
         factored = tm.svr_gather > 0
+        issued_flop = issued_fp64_flop(tm)
+        achieved = issued_flop / (tm.ms_svr / 1e3) / 1e12
         traffic = None
         tp = os.path.join(ROOT, "profiles", "svr_traffic.json")
         if os.path.exists(tp):
@@ -363,7 +373,8 @@ def main():
             "roofline": {"kernel": "k_svr_fact" if factored else "k_svr_dmma", "bound": "tensor", "achieved": achieved, "peak": peak,
                          "unit": "TFLOP/s", "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                          "what": "FP64 pipe (DMMA.8x8x4 + the exp/gather DFMAs share it): flop actually issued by the K-svr launches "
-                                 "(512 per DMMA, 38 per exp element, 4 per gathered triple) over their CUDA-event time",
+                                 "(512 per DMMA, %d per exp element, 4 per gathered triple) over their CUDA-event time"
+                                 % (EXP_FLOP_FACT if factored else EXP_FLOP_DENSE),
                          "issued_flop_per_step": issued_flop / args.steps, "dmma_share_of_issued": tm.svr_dmma * 512.0 / issued_flop,
                          "algorithmic_flop_per_candidate": FLOP_PER_CAND_PER_SV * N_SV,
                          "dense_equivalent_tflops": dense_equiv,
@@ -451,7 +462,7 @@ def target_run(args, rank, local_rank, world, work):
     total_valid = reduce(float(n_valid), dist.ReduceOp.SUM if world > 1 else None)
     if rank == 0:
         peak, peak_src = fp64_peak_tflops()
-        issued = tm.svr_dmma * 512.0 + tm.svr_exp * 38.0 + tm.svr_gather * 4.0
+        issued = issued_fp64_flop(tm)
         print(json.dumps({
             "metric": "candidate MIPs scored/sec (SVR)", "value": total / (ms / 1e3), "unit": "candidates/s", "n_gpus": world,
             "steps": steps, "warmup": warm, "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,

@@ -63,23 +63,47 @@ __device__ __forceinline__ void dmma884(double &c0, double &c1, double a, double
     asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
 }
 
-// same routine as in k_svr.cu (kept local: both kernels inline it)
-__device__ __forceinline__ double exp_nonpos(double t, const double *__restrict__ tab64)
+// tools/ablate_fact.py builds variants with parts of the kernel removed (wrong results, timing only):
+// 1 no exp, 2 no insert-block DMMA, 4 no gather arithmetic, 8 no arm DMMA
+#ifndef MG_FACT_ABLATE
+#define MG_FACT_ABLATE 0
+#endif
+
+// exp of N exponents at once, written stage by stage (N independent chains hide the FP64 latency; same table and
+// polynomial as exp_nonpos in k_svr.cu).  Exponents are <= 0 up to rounding (a few ulp above 0 is harmless);
+// anything below -708, including the -inf of a parked row, is clamped to -708 on the high word (an integer min:
+// magnitudes of negative doubles order like unsigned ints), i.e. contributes < 4e-308 instead of libsvm's 0 --
+// far below one ulp of any score.
+template <int N>
+__device__ __forceinline__ void expn_nonpos(double (&t)[N], const double *__restrict__ tab64)
 {
     const double kMagic = 6755399441055744.0;
-    const double kf0 = fma(t, 92.332482616893657, kMagic);
-    const int k = __double2loint(kf0);
-    const double kf = kf0 - kMagic;
-    double r = fma(kf, -0x1.62e42fee00000p-7, t);
-    r = fma(kf, -0x1.a39ef35793c76p-39, r);
-    double q = fma(r, 1.0 / 120.0, 1.0 / 24.0);
-    q = fma(q, r, 1.0 / 6.0);
-    q = fma(q, r, 0.5);
-    const double p = fma(r * r, q, r);
-    const double tj = tab64[k & 63];
-    const double v = fma(tj, p, tj);
-    const double scaled = __hiloint2double(__double2hiint(v) + ((k >> 6) << 20), __double2loint(v));
-    return t < -708.0 ? 0.0 : scaled;
+    double kf0[N], r[N], q[N];
+#pragma unroll
+    for (int i = 0; i < N; i++) t[i] = __hiloint2double((int)min((unsigned)__double2hiint(t[i]), 0xC0862000u), __double2loint(t[i]));
+#pragma unroll
+    for (int i = 0; i < N; i++) kf0[i] = fma(t[i], 92.332482616893657, kMagic);
+#pragma unroll
+    for (int i = 0; i < N; i++) q[i] = kf0[i] - kMagic;
+#pragma unroll
+    for (int i = 0; i < N; i++) r[i] = fma(q[i], -0x1.62e42fee00000p-7, t[i]);
+#pragma unroll
+    for (int i = 0; i < N; i++) r[i] = fma(q[i], -0x1.a39ef35793c76p-39, r[i]);
+#pragma unroll
+    for (int i = 0; i < N; i++) q[i] = fma(r[i], 1.0 / 120.0, 1.0 / 24.0);
+#pragma unroll
+    for (int i = 0; i < N; i++) q[i] = fma(q[i], r[i], 1.0 / 6.0);
+#pragma unroll
+    for (int i = 0; i < N; i++) q[i] = fma(q[i], r[i], 0.5);
+#pragma unroll
+    for (int i = 0; i < N; i++) r[i] = fma(r[i] * r[i], q[i], r[i]);
+#pragma unroll
+    for (int i = 0; i < N; i++) {
+        const int k = __double2loint(kf0[i]);
+        const double tj = tab64[k & 63];
+        const double v = fma(tj, r[i], tj);
+        t[i] = __hiloint2double(__double2hiint(v) + ((k >> 6) << 20), __double2loint(v));
+    }
 }
 
 constexpr int kThreads = FACT_THREADS, kWarps = FACT_THREADS / 32;
@@ -127,7 +151,7 @@ k_svr_fact(const DevFact *__restrict__ fc, const DevFTask *__restrict__ tasks, i
     // role of the two arm tables on this strand
     const int nA = strand ? n_lig : n_ext, nQ = strand ? n_ext : n_lig;
     const bool ligA = strand != 0, ligQ = strand == 0;  // which arm table plays the ligation role
-    const int RA = (tk.nsi * nA + 7) & ~7, RQ = ((tk.nsi + dsum) * nQ + 7) & ~7, RI = (tk.nsi * n_sums + 7) & ~7;
+    const int RA = (tk.nsi * nA + 15) & ~15, RQ = ((tk.nsi + dsum) * nQ + 15) & ~15, RI = (tk.nsi * n_sums + 15) & ~15;
     const int R = RA + RQ + RI;
 
     // ---- shared memory carve-up (capacities are for the larger of the two strands; host-checked) ----
@@ -168,7 +192,7 @@ k_svr_fact(const DevFact *__restrict__ fc, const DevFTask *__restrict__ tasks, i
     //      represents a row.  Thread t owns candidates t, t + kGatherThreads, ... ----
     const bool gatherer = warp >= kMathWarps && warp < kMathWarps + kGatherWarps;
     const int gt = threadIdx.x - kMathWarps * 32;
-    int ra[kCpt], rq[kCpt], ri[kCpt], state[kCpt];  // state: 0 skipped, 1 invalid (zero row), 2 scored
+    int ra[kCpt], rq[kCpt], ri[kCpt], state[kCpt];  // state: 0 skipped, 1 invalid (zero row), 2 scored, 3 scored with a non-finite feature
     int64_t g[kCpt];
 #pragma unroll
     for (int h = 0; h < kCpt; h++) { ra[h] = rq[h] = ri[h] = state[h] = 0; g[h] = 0; }
@@ -212,8 +236,9 @@ k_svr_fact(const DevFact *__restrict__ fc, const DevFTask *__restrict__ tasks, i
             return;
         }
     }
-    // work units of the math warps: one 8-row fragment x all C columns; longest-processing-time assignment
-    const int uI = RI >> 3, uQ = RQ >> 3, uA = RA >> 3, n_units = uI + uQ + uA;
+    // work units of the math warps: 16 rows x all C columns (8 accumulator chains and 8 independent exp chains per
+    // lane: the epilogue is latency bound); longest-processing-time assignment
+    const int uI = RI >> 4, uQ = RQ >> 4, uA = RA >> 4, n_units = uI + uQ + uA;
     if (threadIdx.x == 0) {
         int load[kMathWarps], cnt[kMathWarps];
         for (int w = 0; w < kMathWarps; w++) load[w] = cnt[w] = 0;
@@ -222,7 +247,7 @@ k_svr_fact(const DevFact *__restrict__ fc, const DevFTask *__restrict__ tasks, i
             for (int w = 0; w < kMathWarps; w++)
                 if (cnt[w] < kUnitsPerWarp && (best < 0 || load[w] < load[best])) best = w;
             unit_list[best * kUnitsPerWarp + cnt[best]++] = (uint8_t)u;
-            load[best] += (u < uI ? FACT_K_INS : FACT_K_ARM) + 24;  // k-steps + epilogue
+            load[best] += (u < uI ? FACT_K_INS : FACT_K_ARM) + 31;  // DMMAs + epilogue (measured: ~31 DMMA times)
         }
         for (int w = 0; w < kMathWarps; w++) unit_cnt[w] = (uint8_t)cnt[w];
     }
@@ -257,14 +282,14 @@ k_svr_fact(const DevFact *__restrict__ fc, const DevFTask *__restrict__ tasks, i
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) ssum += __shfl_xor_sync(0xffffffffu, ssum, o);
         // a non-finite feature (log10(0) = -inf copy) makes every kernel value of the row 0, as in libsvm:
-        // park the row at distance +inf with finite (zero) features so the contraction stays NaN free
+        // park the row at exponent -inf with finite (zero) features so the contraction stays NaN free
         const bool finite = fabs(ssum) <= 1.7976931348623157e308;
 #pragma unroll
         for (int i = 0; i < 3; i++) {
             const int k = i * 32 + lane;
             if (k < ld) dst[k] = finite ? v[i] : 0.0;
         }
-        if (lane == 0) xx[row] = finite ? ssum : __longlong_as_double(0x7ff0000000000000LL);
+        if (lane == 0) xx[row] = finite ? -gamma * ssum : __longlong_as_double(0xfff0000000000000LL);  // exponent scale
         if (role == 1) {
             // junction one-hot 175..190 -> code
             int code = 16;
@@ -276,7 +301,6 @@ k_svr_fact(const DevFact *__restrict__ fc, const DevFTask *__restrict__ tasks, i
     }
     __syncthreads();
 
-    const double ngamma = -gamma;
     if (warp == kMathWarps + kGatherWarps) {
         // =============================== producer warp: SV blobs ===============================
         if (lane == 0) {
@@ -304,45 +328,64 @@ k_svr_fact(const DevFact *__restrict__ fc, const DevFTask *__restrict__ tasks, i
                 int ld, row0;
                 bool is_ins = false, is_lig;
                 if (u < uI) {
-                    F = FI + (u * 8) * FACT_LD_INS; ld = FACT_LD_INS; S = sb + FACT_OFF_INS;
-                    ssb = sb + FACT_OFF_SS + 2 * C; row0 = RA + RQ + u * 8; is_ins = true; is_lig = false;
+                    F = FI + (u * 16) * FACT_LD_INS; ld = FACT_LD_INS; S = sb + FACT_OFF_INS;
+                    ssb = sb + FACT_OFF_SS + 2 * C; row0 = RA + RQ + u * 16; is_ins = true; is_lig = false;
                 } else if (u < uI + uQ) {
                     const int m = u - uI;
-                    F = FQ + (m * 8) * FACT_LD_ARM; ld = FACT_LD_ARM; row0 = RA + m * 8; is_lig = ligQ;
+                    F = FQ + (m * 16) * FACT_LD_ARM; ld = FACT_LD_ARM; row0 = RA + m * 16; is_lig = ligQ;
                     S = sb + (is_lig ? FACT_OFF_LIG : FACT_OFF_EXT); ssb = sb + FACT_OFF_SS + (is_lig ? C : 0);
                 } else {
                     const int m = u - uI - uQ;
-                    F = FA + (m * 8) * FACT_LD_ARM; ld = FACT_LD_ARM; row0 = m * 8; is_lig = ligA;
+                    F = FA + (m * 16) * FACT_LD_ARM; ld = FACT_LD_ARM; row0 = m * 16; is_lig = ligA;
                     S = sb + (is_lig ? FACT_OFF_LIG : FACT_OFF_EXT); ssb = sb + FACT_OFF_SS + (is_lig ? C : 0);
                 }
-                // 4 independent accumulator chains: 2 column fragments x even/odd k.  One 16-byte load serves two
-                // k4 steps: the lane with thread-in-group t holds columns 8i+2t (even step) and 8i+2t+1 (odd step)
-                double a[2][2] = {{0.0, 0.0}, {0.0, 0.0}}, b[2][2] = {{0.0, 0.0}, {0.0, 0.0}};
-                const double2 *fa = reinterpret_cast<const double2 *>(F + gid * ld + 2 * tig);
+                // 8 independent accumulator chains: 2 row fragments x 2 column fragments x even/odd k.  The even chains
+                // start from -gamma (||row||^2 + ||s||^2 [+ junction term]) (pre-scaled tables; the SV blocks carry the
+                // factor 2 gamma), so the contraction ends on the exponent itself.  One 16-byte load serves two k4 steps:
+                // thread-in-group t holds columns 8i+2t (even step) and 8i+2t+1 (odd step)
+                double a[2][2][2], b[2][2][2];
+#pragma unroll
+                for (int mf = 0; mf < 2; mf++) {
+                    const int row = row0 + mf * 8 + gid;
+                    const double xr = xx[row];
+                    const double *tb = is_lig ? sb + FACT_OFF_JT + jc[row] * C : ssb;
+#pragma unroll
+                    for (int nf = 0; nf < 2; nf++) {
+                        const double2 tv = *reinterpret_cast<const double2 *>(tb + nf * 8 + 2 * tig);
+                        a[mf][nf][0] = xr + tv.x; a[mf][nf][1] = xr + tv.y;
+                        b[mf][nf][0] = b[mf][nf][1] = 0.0;
+                    }
+                }
+                const double2 *f0 = reinterpret_cast<const double2 *>(F + gid * ld + 2 * tig);
+                const double2 *f1 = reinterpret_cast<const double2 *>(F + (8 + gid) * ld + 2 * tig);
                 const double2 *s0 = reinterpret_cast<const double2 *>(S + gid * ld + 2 * tig);
                 const double2 *s1 = reinterpret_cast<const double2 *>(S + (8 + gid) * ld + 2 * tig);
+                const bool skip = ((MG_FACT_ABLATE & 2) && is_ins) || ((MG_FACT_ABLATE & 8) && !is_ins);
 #pragma unroll 3
                 for (int it = 0; it < ld / 8; it++) {
-                    const double2 f = fa[it * 4], p0 = s0[it * 4], p1 = s1[it * 4];
-                    dmma884(a[0][0], a[0][1], f.x, p0.x);
-                    dmma884(a[1][0], a[1][1], f.x, p1.x);
-                    dmma884(b[0][0], b[0][1], f.y, p0.y);
-                    dmma884(b[1][0], b[1][1], f.y, p1.y);
+                    if (skip) break;
+                    const double2 x0 = f0[it * 4], x1 = f1[it * 4], p0 = s0[it * 4], p1 = s1[it * 4];
+                    dmma884(a[0][0][0], a[0][0][1], x0.x, p0.x);
+                    dmma884(a[0][1][0], a[0][1][1], x0.x, p1.x);
+                    dmma884(a[1][0][0], a[1][0][1], x1.x, p0.x);
+                    dmma884(a[1][1][0], a[1][1][1], x1.x, p1.x);
+                    dmma884(b[0][0][0], b[0][0][1], x0.y, p0.y);
+                    dmma884(b[0][1][0], b[0][1][1], x0.y, p1.y);
+                    dmma884(b[1][0][0], b[1][0][1], x1.y, p0.y);
+                    dmma884(b[1][1][0], b[1][1][1], x1.y, p1.y);
                 }
-                const int row = row0 + gid;
-                const double base = xx[row];
-                const double *jt = sb + FACT_OFF_JT + (is_lig ? jc[row] : 16) * C;
-                double *er = Eb + row * EST;
+                // epilogue, stage by stage over the lane's 8 elements so that 8 exp chains are in flight
+                double t[8];
 #pragma unroll
-                for (int nf = 0; nf < 2; nf++) {
-                    const int c0 = nf * 8 + 2 * tig;
-                    const double d0 = fmax(fma(-2.0, a[nf][0] + b[nf][0], base + ssb[c0] + jt[c0]), 0.0);
-                    const double d1 = fmax(fma(-2.0, a[nf][1] + b[nf][1], base + ssb[c0 + 1] + jt[c0 + 1]), 0.0);
-                    double e0 = exp_nonpos(ngamma * d0, etab), e1 = exp_nonpos(ngamma * d1, etab);
-                    if (is_ins) { e0 *= ws[c0]; e1 *= ws[c0 + 1]; }
-                    er[c0] = e0;
-                    er[c0 + 1] = e1;
+                for (int i = 0; i < 8; i++) t[i] = a[i >> 2][(i >> 1) & 1][i & 1] + b[i >> 2][(i >> 1) & 1][i & 1];
+                if (!(MG_FACT_ABLATE & 1)) expn_nonpos<8>(t, etab);
+                if (is_ins) {
+#pragma unroll
+                    for (int i = 0; i < 8; i++) t[i] *= ws[((i >> 1) & 1) * 8 + 2 * tig + (i & 1)];
                 }
+#pragma unroll
+                for (int i = 0; i < 8; i++)
+                    Eb[(row0 + (i >> 2) * 8 + gid) * EST + ((i >> 1) & 1) * 8 + 2 * tig + (i & 1)] = t[i];
             }
             __syncwarp();
             if (lane == 0) {
@@ -354,7 +397,12 @@ k_svr_fact(const DevFact *__restrict__ fc, const DevFTask *__restrict__ tasks, i
         // ======================= gather warps: every candidate picks its three factors =======================
         double acc[kCpt];
 #pragma unroll
-        for (int h = 0; h < kCpt; h++) acc[h] = 0.0;
+        for (int h = 0; h < kCpt; h++) {
+            acc[h] = 0.0;
+            // a candidate with a parked (non-finite) row has every kernel value exactly 0, as in libsvm: state 3
+            const double kNegInf = __longlong_as_double(0xfff0000000000000LL);
+            if (state[h] == 2 && (xx[ra[h]] == kNegInf || xx[rq[h]] == kNegInf || xx[ri[h]] == kNegInf)) state[h] = 3;
+        }
         for (int ch = 0; ch < n_chunks; ch++) {
             const int st = ch & 1;
             mbar_wait(&e_full[st], (ch >> 1) & 1);
@@ -365,7 +413,10 @@ k_svr_fact(const DevFact *__restrict__ fc, const DevFTask *__restrict__ tasks, i
                 const double *ea = Eb + ra[h] * EST, *eq = Eb + rq[h] * EST, *ei = Eb + ri[h] * EST;
                 double s = acc[h];
 #pragma unroll
-                for (int i = 0; i < C; i++) s = fma(ea[i] * eq[i], ei[i], s);
+                for (int i = 0; i < C; i++) {
+                    if (MG_FACT_ABLATE & 4) { if (i == 0) s += ea[0] + eq[0] + ei[0]; continue; }
+                    s = fma(ea[i] * eq[i], ei[i], s);
+                }
                 acc[h] = s;
             }
             __syncwarp();
@@ -375,7 +426,7 @@ k_svr_fact(const DevFact *__restrict__ fc, const DevFTask *__restrict__ tasks, i
         for (int h = 0; h < kCpt; h++) {
             const int t = gt + h * kGatherThreads;
             if (t < n_c)
-                out[g[h]] = state[h] == 2 ? acc[h] - rho : (state[h] == 1 ? zero_score : __longlong_as_double(0x7ff8000000000000LL));
+                out[g[h]] = state[h] >= 2 ? acc[h] - rho : (state[h] == 1 ? zero_score : __longlong_as_double(0x7ff8000000000000LL));
         }
     }
 }
@@ -416,7 +467,7 @@ int launch_svr_fact(mg_ctx *ctx, const mg_panel *p, int ftask0, int ftask1, cons
         for (int t = ftask0; t < ftask1; t++) {
             const DevFTask &tk = p->h_ftasks[t];
             const int nA = tk.strand ? f.n_lig : f.n_ext, nQ = tk.strand ? f.n_ext : f.n_lig;
-            const int RA = (tk.nsi * nA + 7) & ~7, RQ = ((tk.nsi + h.max_sum - h.min_sum) * nQ + 7) & ~7, RI = (tk.nsi * f.n_sums + 7) & ~7;
+            const int RA = (tk.nsi * nA + 15) & ~15, RQ = ((tk.nsi + h.max_sum - h.min_sum) * nQ + 15) & ~15, RI = (tk.nsi * f.n_sums + 15) & ~15;
             dmma += chunks * ((RA + RQ) / 8 * (FACT_K_ARM / 4) + RI / 8 * (FACT_K_INS / 4)) * (FACT_C / 8);
             ex += chunks * (RA + RQ + RI) * FACT_C;
             ga += chunks * tk.nsi * f.n_pairs * FACT_C;

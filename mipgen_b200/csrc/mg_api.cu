@@ -417,7 +417,7 @@ extern "C" int mg_set_config(mg_ctx *ctx, const mg_config *c)
             f->n_pairs = c->n_pairs; f->n_cap = h.n_cap; f->n_ext = (int)exts.size(); f->n_lig = (int)ligs.size();
             f->n_sums = (int)sums.size(); f->min_sum = h.min_sum; f->max_sum = h.max_sum;
             const int dsum = h.max_sum - h.min_sum;
-            auto pad8 = [](int v) { return (v + 7) & ~7; };
+            auto pad8 = [](int v) { return (v + 15) & ~15; };  // the factored kernel's work units are 16 rows
             for (int W = 8; W >= 1 && !ctx->fact_ok; W /= 2) {
                 if (W * c->n_pairs > FACT_CPT * FACT_GATHER_WARPS * 32) continue;  // FACT_CPT candidates per gather thread
                 const int RA0 = pad8(W * f->n_ext), RA1 = pad8(W * f->n_lig);
@@ -426,7 +426,7 @@ extern "C" int mg_set_config(mg_ctx *ctx, const mg_config *c)
                 f->cap_FQ = std::max(RQ0, RQ1) * FACT_LD_ARM;
                 f->cap_FI = RI * FACT_LD_INS;
                 f->cap_R = std::max(RA0 + RQ0, RA1 + RQ1) + RI;
-                if (f->cap_R / 8 > FACT_MATH_WARPS * 24) continue;  // per-warp work-unit lists
+                if (f->cap_R / 16 > FACT_MATH_WARPS * 24) continue;  // per-warp work-unit lists
                 size_t doubles = (size_t)f->cap_FA + f->cap_FQ + f->cap_FI + f->cap_R + 2 * (size_t)f->cap_R * (FACT_C + 1) + 2 * FACT_BLOB +
                                  2 * FACT_C + 64;
                 size_t bytes = doubles * 8 + 64 + (size_t)f->cap_R * 8 + FACT_MATH_WARPS * 25 + 64;  // + mbarriers, rep[] and jc[] ints, unit lists
@@ -489,16 +489,21 @@ static int upload_model(mg_ctx *ctx, const std::vector<double> &dense, const std
             double *b = &blob[(size_t)(i / FACT_C) * FACT_BLOB];
             const int r = i % FACT_C;
             const double *srow = &sv[(size_t)i * MG_NFEAT];
+            // the blocks carry the factor 2 gamma and the norm tables the factor -gamma, so the kernel's
+            // contraction  -g ||x||^2 - g ||s||^2 + (2 g s) . x  ends on the exponent itself
+            const double g2 = 2.0 * gamma;
             double se = 0, sl = 0, si = 0;
-            for (int k = 0; k < 22; k++) { b[FACT_OFF_EXT + r * FACT_LD_ARM + k] = srow[k]; se += srow[k] * srow[k]; }
-            b[FACT_OFF_EXT + r * FACT_LD_ARM + 22] = srow[190]; se += srow[190] * srow[190];
-            for (int k = 0; k < 22; k++) { b[FACT_OFF_LIG + r * FACT_LD_ARM + k] = srow[152 + k]; sl += srow[152 + k] * srow[152 + k]; }
-            b[FACT_OFF_LIG + r * FACT_LD_ARM + 22] = srow[191]; sl += srow[191] * srow[191];
-            // junction one-hot (features 175..190): ||onehot(jc) - s||^2 = sum_j s_j^2 + (1 - 2 s_jc)
-            for (int k = 0; k < 16; k++) { sl += srow[174 + k] * srow[174 + k]; b[FACT_OFF_JT + k * FACT_C + r] = 1.0 - 2.0 * srow[174 + k]; }
-            b[FACT_OFF_JT + 16 * FACT_C + r] = 0.0;
-            for (int k = 0; k < 86; k++) { b[FACT_OFF_INS + r * FACT_LD_INS + k] = srow[66 + k]; si += srow[66 + k] * srow[66 + k]; }
-            b[FACT_OFF_SS + r] = se; b[FACT_OFF_SS + FACT_C + r] = sl; b[FACT_OFF_SS + 2 * FACT_C + r] = si;
+            for (int k = 0; k < 22; k++) { b[FACT_OFF_EXT + r * FACT_LD_ARM + k] = g2 * srow[k]; se += srow[k] * srow[k]; }
+            b[FACT_OFF_EXT + r * FACT_LD_ARM + 22] = g2 * srow[190]; se += srow[190] * srow[190];
+            for (int k = 0; k < 22; k++) { b[FACT_OFF_LIG + r * FACT_LD_ARM + k] = g2 * srow[152 + k]; sl += srow[152 + k] * srow[152 + k]; }
+            b[FACT_OFF_LIG + r * FACT_LD_ARM + 22] = g2 * srow[191]; sl += srow[191] * srow[191];
+            // junction one-hot (features 175..190): ||onehot(jc) - s||^2 = sum_j s_j^2 + (1 - 2 s_jc); the table row of
+            // junction code jc holds the whole ligation-role term, row 16 the one for "no junction bit set"
+            for (int k = 0; k < 16; k++) sl += srow[174 + k] * srow[174 + k];
+            for (int k = 0; k < 16; k++) b[FACT_OFF_JT + k * FACT_C + r] = -gamma * (sl + (1.0 - 2.0 * srow[174 + k]));
+            b[FACT_OFF_JT + 16 * FACT_C + r] = -gamma * sl;
+            for (int k = 0; k < 86; k++) { b[FACT_OFF_INS + r * FACT_LD_INS + k] = g2 * srow[66 + k]; si += srow[66 + k] * srow[66 + k]; }
+            b[FACT_OFF_SS + r] = -gamma * se; b[FACT_OFF_SS + FACT_C + r] = -gamma * sl; b[FACT_OFF_SS + 2 * FACT_C + r] = -gamma * si;
         }
         CUDA_TRY(ctx, cudaMalloc(&ctx->d_fact_blob, blob.size() * 8));
         CUDA_TRY(ctx, cudaMemcpy(ctx->d_fact_blob, blob.data(), blob.size() * 8, cudaMemcpyHostToDevice));
