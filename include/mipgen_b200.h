@@ -18,6 +18,7 @@
  *   mg_panel_*              mipgen::tile_regions + design_mip      mipgen.cpp:599-613
  *                           (Plus/Minus geometry and setters)      PlusSVMipv4.cpp:7-28, MinusSVMipv4.cpp:6-51
  *   mg_tile_replay          the score-dependent skips of the loop  mipgen.cpp:426-437, 494-497
+ *   mg_describe_candidates, mg_format_mip_record   print_details   mipgen.cpp:765-794
  *
  * Threading: a context is used by one host thread at a time; calls are
  * synchronous unless stated.  The library never calls rand()/srand() and never
@@ -207,6 +208,41 @@ int mg_panel_select(mg_ctx *ctx, mg_panel *p, const mg_select_params *sp, int64_
  * a bad config.  Pure host logic: needs no context and no device. */
 int64_t mg_tile_replay(const mg_config *cfg, const mg_region *r, const uint8_t *valid, const double *score,
                        int method, int heuristic, double upper_score_limit, int64_t *out_idx, int64_t cap);
+
+/* ---- design-file records for the batched caller ------------------------------
+ * A caller that owns the loop (INTEGRATION.md route B) turns grid indices -- the enumeration from
+ * mg_tile_replay, the winners from mg_panel_select -- back into what the reference keeps per SVMipv4 object and
+ * prints with print_details (mipgen.cpp:765-794).  Host arithmetic only. */
+typedef struct mg_mip_info {
+    int strand;                     /* 0 '+', 1 '-' */
+    int ext_len, lig_len;           /* extension_arm_length, ligation_arm_length */
+    int scan_start, scan_stop;      /* scan_start_position, scan_stop_position (chromosomal, 1-based) */
+    int ext_start, ext_stop;        /* ext_probe_start/stop  (PlusSVMipv4.cpp:7-14, MinusSVMipv4.cpp:30-37) */
+    int lig_start, lig_stop;        /* lig_probe_start/stop */
+    int ext_copy, lig_copy;         /* ext/lig_probe_copy (mipgen.cpp:612-613); 1 without a copy table */
+} mg_mip_info;
+
+/* Geometry and arm copy numbers of n candidates of one region, given their grid indices.  Returns MG_OK or
+ * MG_ERR_INVALID (bad config / index outside the region's grid). */
+int mg_describe_candidates(const mg_config *cfg, const mg_region *r, const int64_t *idx, int n, mg_mip_info *out);
+
+/* One record exactly as print_details writes it to all_mips.txt / collapsed_mips.txt (mipgen.cpp:765-794):
+ * key, score (ostream default = %g), chr, arm coordinates / copies / sequences (reverse-complemented on '-',
+ * MinusSVMipv4.cpp:38-51), scan target, mip_seq = lig + universal_middle + ext (mipgen.cpp:605), feature
+ * start - 1 and stop, strand, failure flags "000" (no SNP / TRF / mapping inputs), label_%04d.
+ * universal_middle is mipgen.cpp:199-200's string (lig tag Ns + constant + ext tag Ns).
+ * Writes at most cap bytes incl. the terminating NUL; returns the record's length (without NUL), or -1. */
+int64_t mg_format_mip_record(const mg_region *r, const mg_mip_info *m, double score, const char *chr, const char *label,
+                             int feature_start, int feature_stop, const char *universal_middle, int mip_index,
+                             char *buf, int64_t cap);
+
+/* The same for n candidates of one region at once (grid indices idx, scores taken from the region's score grid),
+ * numbered first_index, first_index + 1, ...: what output_collapsed_mips (mipgen.cpp:1651-1668) or the all_mips
+ * writer (mipgen.cpp:474, 488) appends for one feature.  Returns the bytes written (no NUL is appended), or -1 if
+ * cap is too small or an argument is invalid; 512 + 3 * max_capture bytes per record are always enough. */
+int64_t mg_format_mip_records(const mg_config *cfg, const mg_region *r, const int64_t *idx, int n, const double *score,
+                              const char *chr, const char *label, int feature_start, int feature_stop,
+                              const char *universal_middle, int first_index, char *buf, int64_t cap);
 
 #ifdef __cplusplus
 }

@@ -47,6 +47,11 @@ class MgSelectParams(C.Structure):
                 ("upper_score_limit", C.c_double), ("max_arm_copy", C.c_int), ("target_arm_copy", C.c_int)]
 
 
+class MgMipInfo(C.Structure):
+    _fields_ = [(n, C.c_int) for n in ("strand", "ext_len", "lig_len", "scan_start", "scan_stop", "ext_start", "ext_stop",
+                                        "lig_start", "lig_stop", "ext_copy", "lig_copy")]
+
+
 class MgTimings(C.Structure):
     _fields_ = [("ms_feat", C.c_double), ("launches_feat", C.c_long), ("ms_svr", C.c_double),
                 ("launches_svr", C.c_long), ("ms_other", C.c_double), ("launches_other", C.c_long),
@@ -94,6 +99,11 @@ SYMBOLS = [
     ("mg_panel_select", C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(MgSelectParams), c_int64_p, c_int64_p]),
     ("mg_tile_replay", C.c_int64, [C.POINTER(MgConfig), C.POINTER(MgRegion), c_ubyte_p, c_double_p, C.c_int, C.c_int,
                                    C.c_double, c_int64_p, C.c_int64]),
+    ("mg_describe_candidates", C.c_int, [C.POINTER(MgConfig), C.POINTER(MgRegion), c_int64_p, C.c_int, C.POINTER(MgMipInfo)]),
+    ("mg_format_mip_records", C.c_int64, [C.POINTER(MgConfig), C.POINTER(MgRegion), c_int64_p, C.c_int, c_double_p, C.c_char_p,
+                                          C.c_char_p, C.c_int, C.c_int, C.c_char_p, C.c_int, C.c_char_p, C.c_int64]),
+    ("mg_format_mip_record", C.c_int64, [C.POINTER(MgRegion), C.POINTER(MgMipInfo), C.c_double, C.c_char_p, C.c_char_p, C.c_int,
+                                         C.c_int, C.c_char_p, C.c_int, C.c_char_p, C.c_int64]),
 ]
 
 _lib = None
@@ -165,6 +175,34 @@ def tile_replay(cfg: Config, r: Region, valid: np.ndarray, score: np.ndarray, me
     if n < 0:
         raise MgError("mg_tile_replay: bad config")
     return out[:n]
+
+
+UNIVERSAL_CONSTANT = "CTTCAGCTTCCCGATATCCGACGGTAGTGT"  # mipgen.cpp:199
+
+
+def universal_middle(lig_tag_length: int = 0, ext_tag_length: int = 5) -> str:
+    """mipgen.cpp:200 (defaults of -lig_tag_sizes / -ext_tag_sizes)."""
+    return "N" * lig_tag_length + UNIVERSAL_CONSTANT + "N" * ext_tag_length
+
+
+def design_records(cfg: Config, r: Region, idx: np.ndarray, score: np.ndarray, chrom: str, label: str, feature_start: int,
+                   feature_stop: int, first_index: int, middle: Optional[str] = None, raw: bool = False):
+    """The all_mips.txt / collapsed_mips.txt lines of region r's candidates idx (grid indices, in output order),
+    numbered from first_index (mg_format_mip_records; no device needed).  Returns str, or with raw=True a
+    memoryview over the C buffer."""
+    lib = load_library()
+    c, _k = _c_config(cfg)
+    arr, _k2 = _c_regions([r])
+    idx = np.ascontiguousarray(idx, np.int64)
+    score = np.ascontiguousarray(score, np.float64)
+    mid = (middle if middle is not None else universal_middle()).encode()
+    cap = max(1, idx.size) * (512 + 3 * cfg.max_capture + len(mid) + len(label) + len(chrom))
+    buf = C.create_string_buffer(cap)
+    n = lib.mg_format_mip_records(C.byref(c), arr, _ptr(idx, c_int64_p), idx.size, _ptr(score, c_double_p), chrom.encode(),
+                                  label.encode(), feature_start, feature_stop, mid, first_index, buf, cap)
+    if n < 0:
+        raise MgError("mg_format_mip_records: bad config, grid index or buffer")
+    return memoryview(buf)[:n] if raw else buf.raw[:n].decode()  # raw: no copy, for writing large files
 
 
 class Panel:

@@ -1159,3 +1159,99 @@ extern "C" int64_t mg_tile_replay(const mg_config *cfg, const mg_region *r, cons
     }
     return n;
 }
+
+// ---------------------------------------------------------------------------
+// host helpers: grid index -> the fields of an SVMipv4 object -> a design-file record
+// ---------------------------------------------------------------------------
+extern "C" int mg_describe_candidates(const mg_config *cfg, const mg_region *r, const int64_t *idx, int n, mg_mip_info *out)
+{
+    HostConfig c;
+    std::string err;
+    if (!r || (n > 0 && (!idx || !out)) || host_config_from(cfg, c, err) != MG_OK) return MG_ERR_INVALID;
+    const int n_pairs = (int)c.ext_len.size(), ns = n_scan(c, r), s0 = first_scan_start(c, r);
+    const int64_t grid = (int64_t)ns * c.n_cap * n_pairs * 2;
+    auto copy_of = [&](int start, int len) {  // mipgen.cpp:612-613; an absent key reads as 0
+        if (!r->copies) return 1;
+        for (size_t k = 0; k < c.oligo_sizes.size(); k++)
+            if (c.oligo_sizes[k] == len) {
+                const int i = start - r->seq_start;
+                return (i < 0 || i >= r->seq_len) ? 0 : r->copies[(int64_t)k * r->seq_len + i];
+            }
+        return 0;
+    };
+    for (int k = 0; k < n; k++) {
+        int64_t q = idx[k];
+        if (q < 0 || q >= grid) return MG_ERR_INVALID;
+        mg_mip_info &m = out[k];
+        m.strand = (int)(q & 1); q >>= 1;
+        const int p = (int)(q % n_pairs); q /= n_pairs;
+        const int ci = (int)(q % c.n_cap), si = (int)(q / c.n_cap);
+        m.ext_len = c.ext_len[p]; m.lig_len = c.lig_len[p];
+        m.scan_start = s0 + si;
+        m.scan_stop = m.scan_start + (c.max_capture - ci * c.inc) - m.ext_len - m.lig_len - 1;
+        if (m.strand == 0) {  // PlusSVMipv4.cpp:7-14
+            m.ext_start = m.scan_start - m.ext_len; m.ext_stop = m.scan_start - 1;
+            m.lig_start = m.scan_stop + 1; m.lig_stop = m.scan_stop + m.lig_len;
+        } else {              // MinusSVMipv4.cpp:30-37
+            m.lig_start = m.scan_start - m.lig_len; m.lig_stop = m.scan_start - 1;
+            m.ext_start = m.scan_stop + 1; m.ext_stop = m.scan_stop + m.ext_len;
+        }
+        m.ext_copy = copy_of(m.ext_start, m.ext_len);
+        m.lig_copy = copy_of(m.lig_start, m.lig_len);
+    }
+    return MG_OK;
+}
+
+extern "C" int64_t mg_format_mip_record(const mg_region *r, const mg_mip_info *m, double score, const char *chr, const char *label,
+                                        int feature_start, int feature_stop, const char *universal_middle, int mip_index,
+                                        char *buf, int64_t cap)
+{
+    if (!r || !r->seq || !m || !chr || !label || !universal_middle || !buf || cap <= 0) return -1;
+    // the three strings as the object holds them: genomic on '+', reverse-complemented on '-'
+    auto cut = [&](int start, int stop, std::string &out) {
+        const int a = start - r->seq_start, n = stop - start + 1;
+        if (a < 0 || n < 0 || a + n > r->seq_len) return false;
+        out.assign(r->seq + a, (size_t)n);
+        if (m->strand) {
+            std::reverse(out.begin(), out.end());
+            for (char &ch : out) ch = ch == 'A' ? 'T' : ch == 'C' ? 'G' : ch == 'G' ? 'C' : ch == 'T' ? 'A' : ch;  // MinusSVMipv4.cpp:6-29
+        }
+        return true;
+    };
+    std::string ext, lig, tgt;
+    if (!cut(m->ext_start, m->ext_stop, ext) || !cut(m->lig_start, m->lig_stop, lig) || !cut(m->scan_start, m->scan_stop, tgt)) return -1;
+    const char strand = m->strand ? '-' : '+';
+    char head[256], mid[192], tail[160];
+    snprintf(head, sizeof head, "%s:%d-%d/%d,%d/%c\t%g\t%s\t%d\t%d\t%d\t", chr, m->strand ? m->lig_start : m->ext_start,
+             m->strand ? m->ext_stop : m->lig_stop, m->ext_len, m->lig_len, strand, score, chr, m->ext_start, m->ext_stop, m->ext_copy);
+    snprintf(mid, sizeof mid, "\t%d\t%d\t%d\t", m->lig_start, m->lig_stop, m->lig_copy);
+    std::string rec = head;
+    rec += ext; rec += mid; rec += lig;
+    snprintf(mid, sizeof mid, "\t%d\t%d\t", m->scan_start, m->scan_stop);
+    rec += mid; rec += tgt; rec += '\t';
+    rec += lig; rec += universal_middle; rec += ext;
+    snprintf(tail, sizeof tail, "\t%d\t%d\t%c\t000\t", feature_start - 1, feature_stop, strand);
+    rec += tail; rec += label;
+    snprintf(tail, sizeof tail, "_%04d\n", mip_index);
+    rec += tail;
+    if ((int64_t)rec.size() + 1 > cap) return -1;
+    memcpy(buf, rec.c_str(), rec.size() + 1);
+    return (int64_t)rec.size();
+}
+
+extern "C" int64_t mg_format_mip_records(const mg_config *cfg, const mg_region *r, const int64_t *idx, int n, const double *score,
+                                         const char *chr, const char *label, int feature_start, int feature_stop,
+                                         const char *universal_middle, int first_index, char *buf, int64_t cap)
+{
+    if (n < 0 || (n > 0 && (!idx || !score || !buf))) return -1;
+    std::vector<mg_mip_info> info((size_t)n);
+    if (mg_describe_candidates(cfg, r, idx, n, info.data()) != MG_OK) return -1;
+    int64_t at = 0;
+    for (int k = 0; k < n; k++) {
+        const int64_t len = mg_format_mip_record(r, &info[k], score[idx[k]], chr, label, feature_start, feature_stop, universal_middle,
+                                                 first_index + k, buf + at, cap - at);
+        if (len < 0) return -1;
+        at += len;  // the next record overwrites this one's NUL
+    }
+    return at;
+}

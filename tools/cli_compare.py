@@ -1,7 +1,9 @@
 #!/usr/bin/env python3
-"""Wall-clock comparison of the unmodified reference CLI (oracle/_ref/mipgen) and the drop-in CLI
-(mipgen_b200/dropin/_build/mipgen: the same mipgen.cpp against the GPU library) on one synthetic panel.
-Outputs must be byte-identical; prints the timings as JSON.   python tools/cli_compare.py [n_regions] [n_sv]
+"""Wall-clock comparison of the unmodified reference CLI (oracle/_ref/mipgen), the drop-in CLI
+(mipgen_b200/dropin/_build/mipgen: the same mipgen.cpp against the GPU library) and the batched caller
+(INTEGRATION.md route B: mg_panel_score + mg_panel_select + mg_format_mip_records, which writes collapsed_mips.txt
+itself) on one synthetic panel.  Outputs must be byte-identical; prints the timings as JSON.
+    python tools/cli_compare.py [n_regions] [n_sv]
 """
 import filecmp
 import json
@@ -26,7 +28,7 @@ NEW = os.path.join(ROOT, "mipgen_b200", "dropin", "_build", "mipgen")
 STUB = os.path.join(ROOT, "oracle", "_ref")
 
 
-def run(binary, d, name, bed, gdir, model, extra):
+def run(binary, d, name, bed, gdir, model, extra, silent=True):
     rd = os.path.join(d, name)
     os.makedirs(rd)
     os.symlink(binary, os.path.join(rd, "mipgen"))
@@ -34,12 +36,64 @@ def run(binary, d, name, bed, gdir, model, extra):
     env = dict(os.environ, PATH=STUB + os.pathsep + os.environ["PATH"], MIPGEN_B200_VERBOSE="1")
     t0 = time.perf_counter()
     r = subprocess.run([os.path.join(rd, "mipgen"), "-regions_to_scan", bed, "-project_name", "p", "-bwa_genome_index",
-                        os.path.join(gdir, "chr1.fa"), "-genome_dir", gdir, "-min_capture_size", "162", "-max_capture_size", "162",
-                        "-silent_mode", "on"] + extra, cwd=rd, env=env, capture_output=True, text=True)
+                        os.path.join(gdir, "chr1.fa"), "-genome_dir", gdir, "-min_capture_size", "162", "-max_capture_size", "162"] +
+                       (["-silent_mode", "on"] if silent else []) + extra, cwd=rd, env=env, capture_output=True, text=True)
     dt = time.perf_counter() - t0
     assert r.returncode == 0, r.stderr[-1500:]
     # time of the tile phase: from the first "[mipgen] feature #" line on is not separable here; report total
     return rd, dt, [l for l in r.stderr.splitlines() if "device batches" in l]
+
+
+HEADER = (">mip_key\t%s_score\tchr\text_probe_start\text_probe_stop\text_probe_copy\text_probe_sequence\tlig_probe_start\t"
+          "lig_probe_stop\tlig_probe_copy\tlig_probe_sequence\tmip_scan_start_position\tmip_scan_stop_position\t"
+          "scan_target_sequence\tmip_sequence\tfeature_start_position\tfeature_stop_position\tprobe_strand\tfailure_flags\tmip_name\n")
+
+
+def batched(cfg, regions, mode, model, out_all, out_collapsed):
+    """all_mips.txt and collapsed_mips.txt through the batched caller; returns the stage timings in seconds."""
+    import mipgen_b200 as mg
+    t = {}
+    t0 = time.perf_counter()
+    ctx = mg.Context(0)
+    ctx.set_config(cfg)
+    method = 1 if mode == "svr" else 0
+    if method:
+        ctx.load_svr_model(model)
+    t["context_and_model_s"] = time.perf_counter() - t0
+    t1 = time.perf_counter()
+    for r in regions:
+        r.lrc = ctx.long_range_content(r.flank_seq, r.seq_start, r.seq_stop)
+    pnl = ctx.panel(regions)
+    pnl.score(mg.MG_WANT_SVR if method else mg.MG_WANT_LOGISTIC)
+    valid, lo, sv, _f = pnl.fetch(valid=True, logistic=not method, svr=bool(method))
+    lower, upper = (1.5, 2.2) if method else (0.9, 0.98)  # mipgen.cpp:210-216
+    _so, _sb, po, pb = pnl.select(regions, method, lower, upper)
+    ctx.sync()
+    t["upload_score_select_fetch_s"] = time.perf_counter() - t1
+    t2 = time.perf_counter()
+    score = sv if method else lo
+    offs = pnl.offsets
+    n = n_all = 0
+    f_col, f_all = open(out_collapsed, "wb"), open(out_all, "wb")
+    f_col.write((HEADER % mode).encode())
+    f_all.write((HEADER % mode).encode())
+    for i, r in enumerate(regions):
+        a, b = offs[i], offs[i + 1]
+        local = pb[po[i]:po[i + 1]].reshape(-1)
+        winners = local[local >= 0] - a
+        f_col.write(mg.design_records(cfg, r, winners, score[a:b], "1", r.label, r.start_flanked, r.stop_flanked, n + 1, raw=True))
+        n += winners.size
+        # all_mips.txt: every candidate the tile loop enumerates, in its order (mipgen.cpp:426-497)
+        enum_idx = mg.tile_replay(cfg, r, valid[a:b], score[a:b], method, True, upper)
+        f_all.write(mg.design_records(cfg, r, enum_idx, score[a:b], "1", r.label, r.start_flanked, r.stop_flanked, n_all + 1, raw=True))
+        n_all += enum_idx.size
+    f_col.close()
+    f_all.close()
+    t["format_and_write_s"] = time.perf_counter() - t2
+    t["total_s"] = time.perf_counter() - t0
+    t["collapsed_records"] = n
+    t["all_mips_records"] = n_all
+    return {k: (round(v, 3) if isinstance(v, float) else v) for k, v in t.items()}
 
 
 def main():
@@ -72,8 +126,17 @@ def main():
         b, tb, log = run(NEW, d, "b200_" + mode, bed_m, gdir, model, extra)
         same = all(filecmp.cmp(os.path.join(a, "p." + f), os.path.join(b, "p." + f), shallow=False)
                    for f in ("picked_mips.txt", "collapsed_mips.txt", "snp_mips.txt"))
+        # default (non-silent) run of the reference: it also writes all_mips.txt and the collapsed records
+        c, tc, _ = run(REF, d, "ref_full_" + mode, bed_m, gdir, model, extra, silent=False)
+        f_all, f_col = os.path.join(d, "batched_%s_all.txt" % mode), os.path.join(d, "batched_%s_collapsed.txt" % mode)
+        bt = batched(cfg, regions[:nreg], mode, model, f_all, f_col)
+        same_b = (filecmp.cmp(os.path.join(c, "p.collapsed_mips.txt"), f_col, shallow=False) and
+                  filecmp.cmp(os.path.join(c, "p.all_mips.txt"), f_all, shallow=False))
         out[mode] = {"regions": nreg, "candidates": sum(cfg.grid_size(r) for r in regions[:nreg]), "reference_s": round(ta, 2),
-                     "dropin_s": round(tb, 2), "identical_outputs": same, "shim": log[-1] if log else ""}
+                     "dropin_s": round(tb, 2), "identical_outputs": same, "shim": log[-1] if log else "",
+                     "reference_not_silent_s": round(tc, 2), "batched_caller": bt,
+                     "batched_all_and_collapsed_identical_to_reference": same_b,
+                     "all_mips_bytes": os.path.getsize(f_all)}
     print(json.dumps(out, indent=1))
 
 
