@@ -164,7 +164,7 @@ k_svr_fact(const DevFact *__restrict__ fc, const DevFTask *__restrict__ tasks, i
     double *wst = slab + 2 * FACT_BLOB;     // [2][C] alpha_i * exp(-g d_lrc)
     double *etab = wst + 2 * C;             // [64]
     uint64_t *bars = reinterpret_cast<uint64_t *>(etab + 64);
-    uint64_t *slab_full = bars, *slab_empty = bars + 2, *e_full = bars + 4, *e_empty = bars + 6;
+    uint64_t *slab_full = bars, *e_full = bars + 4, *e_empty = bars + 6;
     int *rep = reinterpret_cast<int *>(bars + 8);              // [cap_R]
     int *jc = rep + fc->cap_R;                                 // [cap_R] junction code of ligation-role rows (16: none)
     uint8_t *unit_list = reinterpret_cast<uint8_t *>(jc + fc->cap_R);  // [kMathWarps][kUnitsPerWarp] units of each math warp
@@ -179,7 +179,6 @@ k_svr_fact(const DevFact *__restrict__ fc, const DevFTask *__restrict__ tasks, i
     if (threadIdx.x == 0) {
         for (int b = 0; b < 2; b++) {
             mbar_init(&slab_full[b], 1);
-            mbar_init(&slab_empty[b], kMathWarps);
             mbar_init(&e_full[b], kMathWarps);
             mbar_init(&e_empty[b], kGatherWarps);
         }
@@ -301,18 +300,15 @@ k_svr_fact(const DevFact *__restrict__ fc, const DevFTask *__restrict__ tasks, i
     }
     __syncthreads();
 
-    if (warp == kMathWarps + kGatherWarps) {
-        // =============================== producer warp: SV blobs ===============================
-        if (lane == 0) {
-            for (int ch = 0; ch < n_chunks; ch++) {
-                const int st = ch & 1;
-                if (ch >= 2) mbar_wait(&slab_empty[st], ((ch >> 1) & 1) ^ 1);
-                mbar_arrive_expect_tx(&slab_full[st], FACT_BLOB * 8 + C * 8);
-                bulk_g2s(slab + st * FACT_BLOB, blob + (int64_t)ch * FACT_BLOB, FACT_BLOB * 8, &slab_full[st]);
-                bulk_g2s(wst + st * C, w_reg + (int64_t)ch * C, C * 8, &slab_full[st]);
-            }
-        }
-    } else if (warp < kMathWarps) {
+    // The SV blob (and the lrc weights) of chunk ch + 2 is fetched by one gather thread as soon as every math warp
+    // has delivered chunk ch (e_full): the math warps arrive there after their last read of that blob buffer.
+    auto fetch_blob = [&](int ch) {
+        const int st = ch & 1;
+        mbar_arrive_expect_tx(&slab_full[st], FACT_BLOB * 8 + C * 8);
+        bulk_g2s(slab + st * FACT_BLOB, blob + (int64_t)ch * FACT_BLOB, FACT_BLOB * 8, &slab_full[st]);
+        bulk_g2s(wst + st * C, w_reg + (int64_t)ch * C, C * 8, &slab_full[st]);
+    };
+    if (warp < kMathWarps) {
         // ======================= math warps: factor tables of the distinct rows =======================
         const int my_units = unit_cnt[warp];
         for (int ch = 0; ch < n_chunks; ch++) {
@@ -388,10 +384,7 @@ k_svr_fact(const DevFact *__restrict__ fc, const DevFTask *__restrict__ tasks, i
                     Eb[(row0 + (i >> 2) * 8 + gid) * EST + ((i >> 1) & 1) * 8 + 2 * tig + (i & 1)] = t[i];
             }
             __syncwarp();
-            if (lane == 0) {
-                mbar_arrive(&e_full[st]);      // this warp's rows of chunk ch are in the table
-                mbar_arrive(&slab_empty[st]);  // and it no longer reads the SV blob of chunk ch
-            }
+            if (lane == 0) mbar_arrive(&e_full[st]);  // this warp's rows of chunk ch are in the table; its reads of the blob are done
         }
     } else {
         // ======================= gather warps: every candidate picks its three factors =======================
@@ -403,9 +396,14 @@ k_svr_fact(const DevFact *__restrict__ fc, const DevFTask *__restrict__ tasks, i
             const double kNegInf = __longlong_as_double(0xfff0000000000000LL);
             if (state[h] == 2 && (xx[ra[h]] == kNegInf || xx[rq[h]] == kNegInf || xx[ri[h]] == kNegInf)) state[h] = 3;
         }
+        if (gt == 0) {
+            fetch_blob(0);
+            if (n_chunks > 1) fetch_blob(1);
+        }
         for (int ch = 0; ch < n_chunks; ch++) {
             const int st = ch & 1;
             mbar_wait(&e_full[st], (ch >> 1) & 1);
+            if (gt == 0 && ch + 2 < n_chunks) fetch_blob(ch + 2);
             const double *Eb = E + st * ESZ;
 #pragma unroll
             for (int h = 0; h < kCpt; h++) {

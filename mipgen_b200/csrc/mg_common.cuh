@@ -111,7 +111,7 @@ __host__ __device__ inline uint32_t fd_pack(uint32_t kind, uint32_t part, uint32
 #define FACT_MATH_WARPS 12
 #define FACT_GATHER_WARPS 4
 #define FACT_CPT 4                                      // candidates per gather thread
-#define FACT_THREADS ((FACT_MATH_WARPS + FACT_GATHER_WARPS + 1) * 32)   // + 1 producer warp
+#define FACT_THREADS ((FACT_MATH_WARPS + FACT_GATHER_WARPS) * 32)       // 16 warps: 128 registers per thread
 #define FACT_K_ARM 24      // 21 arm ratios + arm length + log copy, padded to a multiple of 4 (either role)
 #define FACT_K_INS 88      // 86 insert features
 #define FACT_LD_ARM 24     // strides == 8 mod 16 doubles: conflict-free LDS.128 fragment loads, no padding needed
