@@ -176,6 +176,25 @@ def issued_fp64_flop(tm) -> float:
     return tm.svr_dmma * 512.0 + tm.svr_exp * exp_flop + tm.svr_gather * 4.0
 
 
+_JSON_OUT = None
+
+
+def reserve_stdout():
+    """Keep the process's stdout for the one JSON line: everything else that writes to fd 1 from here on (NCCL's
+    version banner, library chatter) lands on stderr."""
+    global _JSON_OUT
+    if _JSON_OUT is None:
+        sys.stdout.flush()
+        _JSON_OUT = os.fdopen(os.dup(1), "w")
+        os.dup2(2, 1)
+
+
+def emit(line: dict) -> None:
+    out = _JSON_OUT if _JSON_OUT is not None else sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
+
+
 def build_model(ctx, cfg, work: str, n_model_regions: int = 4):
     """2048 SVs = feature rows of random candidates from a different genome seed, alpha ~ U(-1,1),
     calibrated so scores straddle 1.5 / 2.2; written and re-read as a libsvm text model."""
@@ -216,6 +235,7 @@ def main():
                     help="cfg3 (default): 60-region exon panel per GPU, capture 162.  target1mb: the north star's target run -- "
                          "4000 regions (~1 Mb), capture sweep 120..250 step 5 (27 sizes), SVR, regions sharded over the ranks")
     args = ap.parse_args()
+    reserve_stdout()
 
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -393,7 +413,7 @@ def main():
                                     "note": "same panel through the dense candidates x SV contraction (mg_set_svr_mode(1))"}
         if not args.no_cpu_baseline and world == 1:
             line["cpu_baseline"] = cpu_baseline(cfg, model_path, regions[0].lrc, genome)
-        print(json.dumps(line))
+        emit(line)
     pnl.close()
     ctx.close()
     if world > 1:
@@ -463,7 +483,7 @@ def target_run(args, rank, local_rank, world, work):
     if rank == 0:
         peak, peak_src = fp64_peak_tflops()
         issued = issued_fp64_flop(tm)
-        print(json.dumps({
+        emit(({
             "metric": "candidate MIPs scored/sec (SVR)", "value": total / (ms / 1e3), "unit": "candidates/s", "n_gpus": world,
             "steps": steps, "warmup": warm, "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
@@ -502,19 +522,22 @@ def reference_arm(args, rank, world, cfg, work, config):
     path = os.path.join(work, "mipgen_svr.model")
     panel.write_svr_model(path, sv, rng.uniform(-1, 1, N_SV) * 0.05, 1.0 / 192, -1.8)
     bench_genome, _regs = make_panel(cfg, N_REGIONS, GENOME_SEED)
-    vals = []
+    vals, walls = [], []
     last = None
     for _ in range(args.warmup + args.steps):
+        t0 = time.perf_counter()
         last = cpu_baseline(cfg, path, r0.lrc, bench_genome, budget_s=6.0)
+        walls.append((time.perf_counter() - t0) * 1e3)
         vals.append(last["value"])
     v = float(np.mean(vals[args.warmup:])) if len(vals) > args.warmup else float(np.mean(vals))
+    ms_step = float(np.mean(walls[args.warmup:])) if len(walls) > args.warmup else float(np.mean(walls))
     last["value"] = v
     line = {"impl": "reference", "metric": "candidate MIPs scored/sec (SVR)", "value": v, "unit": "candidates/s",
-            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": None, "higher_is_better": True,
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config,
             "cpu_baseline": last,
             "e2e": {"value": v, "unit": "candidates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line))
+    emit(line)
 
 
 if __name__ == "__main__":
