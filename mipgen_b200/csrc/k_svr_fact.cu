@@ -187,53 +187,58 @@ k_svr_fact(const DevFact *__restrict__ fc, const DevFTask *__restrict__ tasks, i
     for (int i = threadIdx.x; i < R; i += kThreads) rep[i] = 0x7fffffff;
     __syncthreads();
 
-    // ---- phase 0 (gather threads): every candidate names its three rows; the lowest candidate index
-    //      represents a row.  Thread t owns candidates t, t + kGatherThreads, ... ----
+    // ---- phase 0 (all threads, one candidate each per round): every candidate names its three rows; the lowest
+    //      candidate index represents a row.  The result is handed to the gather thread that owns the candidate
+    //      (gather thread t owns candidates t, t + kGatherThreads, ...) through the not yet used factor table. ----
     const bool gatherer = warp >= kMathWarps && warp < kMathWarps + kGatherWarps;
     const int gt = threadIdx.x - kMathWarps * 32;
-    int ra[kCpt], rq[kCpt], ri[kCpt], state[kCpt];  // state: 0 skipped, 1 invalid (zero row), 2 scored, 3 scored with a non-finite feature
-    int64_t g[kCpt];
-#pragma unroll
-    for (int h = 0; h < kCpt; h++) { ra[h] = rq[h] = ri[h] = state[h] = 0; g[h] = 0; }
-    if (gatherer) {
-#pragma unroll
-        for (int h = 0; h < kCpt; h++) {
-            const int t = gt + h * kGatherThreads;
-            if (t >= n_c) continue;
-            const int s_rel = t / n_pairs, p = t - s_rel * n_pairs;
-            g[h] = tk.g0 + ((((int64_t)(tk.si0 + s_rel) * n_cap + tk.ci) * n_pairs + p) * 2 + strand);
-            const int e = fc->pair_e[p], l = fc->pair_l[p], sum = e + l;
-            const int ie = fc->ext_idx[e], il = fc->lig_idx[l];
-            ra[h] = strand ? s_rel * n_lig + il : s_rel * n_ext + ie;
-            rq[h] = RA + (strand ? (s_rel + fc->max_sum - sum) * n_ext + ie : (s_rel + fc->max_sum - sum) * n_lig + il);
-            ri[h] = RA + RQ + s_rel * n_sums + fc->sum_idx[sum - fc->min_sum];
-            if (valid[g[h]]) {
-                // feature 22 (extension_arm_length) is zero only in the all-zero row of an invalid candidate
-                state[h] = x[(g[h] - g_base) * MG_NFEAT + 21] == 0.0 ? 1 : 2;
-                if (state[h] == 2) {
-                    atomicMin(&rep[ra[h]], t);
-                    atomicMin(&rep[rq[h]], t);
-                    atomicMin(&rep[ri[h]], t);
-                }
-            }
+    auto grid_index = [&](int t) {  // candidate t of the task -> index in the panel's grid
+        const int s_rel = t / n_pairs, p = t - s_rel * n_pairs;
+        return tk.g0 + ((((int64_t)(tk.si0 + s_rel) * n_cap + tk.ci) * n_pairs + p) * 2 + strand);
+    };
+    int4 *cinfo = reinterpret_cast<int4 *>(E);  // [n_c] {ra, rq, ri, state}; state: 0 skipped, 1 invalid (zero row), 2 scored
+    int any_scored = 0;
+    for (int t = threadIdx.x; t < n_c; t += kThreads) {
+        const int s_rel = t / n_pairs, p = t - s_rel * n_pairs;
+        const int64_t gi = grid_index(t);
+        const uint8_t vd = valid[gi];
+        // feature 22 (extension_arm_length) is zero only in the all-zero row of an invalid candidate
+        const double f22 = vd ? x[(gi - g_base) * MG_NFEAT + 21] : 0.0;
+        const int e = fc->pair_e[p], l = fc->pair_l[p], sum = e + l;
+        const int ie = fc->ext_idx[e], il = fc->lig_idx[l];
+        int4 ci;
+        ci.x = strand ? s_rel * n_lig + il : s_rel * n_ext + ie;
+        ci.y = RA + (strand ? (s_rel + fc->max_sum - sum) * n_ext + ie : (s_rel + fc->max_sum - sum) * n_lig + il);
+        ci.z = RA + RQ + s_rel * n_sums + fc->sum_idx[sum - fc->min_sum];
+        ci.w = vd ? (f22 == 0.0 ? 1 : 2) : 0;
+        if (ci.w == 2) {
+            atomicMin(&rep[ci.x], t);
+            atomicMin(&rep[ci.y], t);
+            atomicMin(&rep[ci.z], t);
+            any_scored = 1;
         }
+        cinfo[t] = ci;
     }
     // a task whose candidates are all skipped or invalid (e.g. a capture size ruled out by mipgen.cpp:429)
     // has no factor tables to build
-    {
-        int any = 0;
+    const bool some = __syncthreads_or(any_scored);
+    int ra[kCpt], rq[kCpt], ri[kCpt], state[kCpt];  // of the gather thread's candidates; state 3: scored with a non-finite feature
 #pragma unroll
-        for (int h = 0; h < kCpt; h++) any |= state[h] == 2;
-        if (!__syncthreads_or(any)) {
-            if (gatherer) {
+    for (int h = 0; h < kCpt; h++) {
+        const int t = gt + h * kGatherThreads;
+        int4 ci = make_int4(0, 0, 0, 0);
+        if (gatherer && t < n_c) ci = cinfo[t];
+        ra[h] = ci.x; rq[h] = ci.y; ri[h] = ci.z; state[h] = ci.w;
+    }
+    if (!some) {
+        if (gatherer) {
 #pragma unroll
-                for (int h = 0; h < kCpt; h++) {
-                    const int t = gt + h * kGatherThreads;
-                    if (t < n_c) out[g[h]] = state[h] == 1 ? zero_score : __longlong_as_double(0x7ff8000000000000LL);
-                }
+            for (int h = 0; h < kCpt; h++) {
+                const int t = gt + h * kGatherThreads;
+                if (t < n_c) out[grid_index(t)] = state[h] == 1 ? zero_score : __longlong_as_double(0x7ff8000000000000LL);
             }
-            return;
         }
+        return;
     }
     // work units of the math warps: 16 rows x all C columns (8 accumulator chains and 8 independent exp chains per
     // lane: the epilogue is latency bound); longest-processing-time assignment
@@ -252,51 +257,57 @@ k_svr_fact(const DevFact *__restrict__ fc, const DevFTask *__restrict__ tasks, i
     }
     __syncthreads();
 
-    // ---- phase 1: copy each row's block out of its representative's feature row; ||row||^2 ----
-    for (int row = warp; row < R; row += kWarps) {
-        const int t = rep[row];
-        int ld, role;  // role 0 ext, 1 lig, 2 ins
-        double *dst;
-        if (row < RA) { ld = FACT_LD_ARM; role = ligA ? 1 : 0; dst = FA + row * FACT_LD_ARM; }
-        else if (row < RA + RQ) { ld = FACT_LD_ARM; role = ligQ ? 1 : 0; dst = FQ + (row - RA) * FACT_LD_ARM; }
-        else { ld = FACT_LD_INS; role = 2; dst = FI + (row - RA - RQ) * FACT_LD_INS; }
-        const double *src = nullptr;
-        if (t != 0x7fffffff) {
-            const int s_rel = t / n_pairs, p = t - s_rel * n_pairs;
-            const int64_t gr = tk.g0 + ((((int64_t)(tk.si0 + s_rel) * n_cap + tk.ci) * n_pairs + p) * 2 + strand);
-            src = x + (gr - g_base) * MG_NFEAT;
-        }
-        double ssum = 0.0, v[3];
+    // ---- phase 1: copy each row's block out of its representative's feature row; -gamma ||row||^2.
+    //      Four rows per warp and round, so that their (dependent, latency-bound) global loads overlap ----
+    constexpr int kRB = 4;
+    for (int rb = warp * kRB; rb < R; rb += kWarps * kRB) {
+        double v[kRB][3], jv[kRB];
+        int ld[kRB], role[kRB];  // role 0 ext, 1 lig, 2 ins
 #pragma unroll
-        for (int i = 0; i < 3; i++) {
-            const int k = i * 32 + lane;
-            v[i] = 0.0;
-            if (src && k < ld) {
-                if (role == 0) v[i] = k < 22 ? src[k] : (k == 22 ? src[190] : 0.0);
-                else if (role == 1) v[i] = k < 22 ? src[152 + k] : (k == 22 ? src[191] : 0.0);
-                else v[i] = k < 86 ? src[66 + k] : 0.0;
+        for (int j = 0; j < kRB; j++) {
+            const int row = rb + j;
+            const int t = row < R ? rep[row] : 0x7fffffff;
+            if (row < RA) { ld[j] = FACT_LD_ARM; role[j] = ligA ? 1 : 0; }
+            else if (row < RA + RQ) { ld[j] = FACT_LD_ARM; role[j] = ligQ ? 1 : 0; }
+            else { ld[j] = FACT_LD_INS; role[j] = 2; }
+            const double *src = t != 0x7fffffff ? x + (grid_index(t) - g_base) * MG_NFEAT : nullptr;
+#pragma unroll
+            for (int i = 0; i < 3; i++) {
+                const int k = i * 32 + lane;
+                v[j][i] = 0.0;
+                if (src && k < ld[j]) {
+                    if (role[j] == 0) v[j][i] = k < 22 ? src[k] : (k == 22 ? src[190] : 0.0);
+                    else if (role[j] == 1) v[j][i] = k < 22 ? src[152 + k] : (k == 22 ? src[191] : 0.0);
+                    else v[j][i] = k < 86 ? src[66 + k] : 0.0;
+                }
             }
-            ssum = fma(v[i], v[i], ssum);
+            jv[j] = (src && role[j] == 1 && lane < 16) ? src[174 + lane] : 0.0;  // junction one-hot 175..190
         }
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) ssum += __shfl_xor_sync(0xffffffffu, ssum, o);
-        // a non-finite feature (log10(0) = -inf copy) makes every kernel value of the row 0, as in libsvm:
-        // park the row at exponent -inf with finite (zero) features so the contraction stays NaN free
-        const bool finite = fabs(ssum) <= 1.7976931348623157e308;
+        for (int j = 0; j < kRB; j++) {
+            const int row = rb + j;
+            if (row >= R) break;
+            double *dst = row < RA ? FA + row * FACT_LD_ARM : row < RA + RQ ? FQ + (row - RA) * FACT_LD_ARM : FI + (row - RA - RQ) * FACT_LD_INS;
+            double ssum = 0.0;
 #pragma unroll
-        for (int i = 0; i < 3; i++) {
-            const int k = i * 32 + lane;
-            if (k < ld) dst[k] = finite ? v[i] : 0.0;
-        }
-        if (lane == 0) xx[row] = finite ? -gamma * ssum : __longlong_as_double(0xfff0000000000000LL);  // exponent scale
-        if (role == 1) {
-            // junction one-hot 175..190 -> code
+            for (int i = 0; i < 3; i++) ssum = fma(v[j][i], v[j][i], ssum);
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) ssum += __shfl_xor_sync(0xffffffffu, ssum, o);
+            // a non-finite feature (log10(0) = -inf copy) makes every kernel value of the row 0, as in libsvm:
+            // park the row at exponent -inf with finite (zero) features so the contraction stays NaN free
+            const bool finite = fabs(ssum) <= 1.7976931348623157e308;
+#pragma unroll
+            for (int i = 0; i < 3; i++) {
+                const int k = i * 32 + lane;
+                if (k < ld[j]) dst[k] = finite ? v[j][i] : 0.0;
+            }
+            if (lane == 0) xx[row] = finite ? -gamma * ssum : __longlong_as_double(0xfff0000000000000LL);  // exponent scale
             int code = 16;
-            if (src && lane < 16 && src[174 + lane] == 1.0) code = lane;
+            if (jv[j] == 1.0) code = lane;
 #pragma unroll
             for (int o = 8; o > 0; o >>= 1) code = min(code, __shfl_xor_sync(0xffffffffu, code, o));
-            if (lane == 0) jc[row] = code;
-        } else if (lane == 0) jc[row] = 16;
+            if (lane == 0) jc[row] = role[j] == 1 ? code : 16;
+        }
     }
     __syncthreads();
 
@@ -424,7 +435,7 @@ k_svr_fact(const DevFact *__restrict__ fc, const DevFTask *__restrict__ tasks, i
         for (int h = 0; h < kCpt; h++) {
             const int t = gt + h * kGatherThreads;
             if (t < n_c)
-                out[g[h]] = state[h] >= 2 ? acc[h] - rho : (state[h] == 1 ? zero_score : __longlong_as_double(0x7ff8000000000000LL));
+                out[grid_index(t)] = state[h] >= 2 ? acc[h] - rho : (state[h] == 1 ? zero_score : __longlong_as_double(0x7ff8000000000000LL));
         }
     }
 }
