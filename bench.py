@@ -247,7 +247,7 @@ def main():
     config = {"workload": "cfg3: %d-region synthetic exon panel per GPU (region length U[%d,%d]), capture 162, 57 arm pairs, "
                           "-score_method svr, %d-SV synthetic RBF model" % (N_REGIONS, LEN_LO, LEN_HI, N_SV),
               "regions_per_gpu": N_REGIONS, "n_sv": N_SV, "sharding": "regions by rank, no collective",
-              "cache": "feature rows in flight (3.2 GB per 2M-candidate chunk) exceed L2; the 3 MB SV matrix is L2-resident by design"}
+              "cache": "feature rows in flight (3.9 GB for the 2.53M-candidate panel; chunks of <= 4M candidates) exceed L2; the 3 MB SV matrix is L2-resident by design"}
 
     if args.impl == "reference":
         return reference_arm(args, rank, world, cfg, work, config)

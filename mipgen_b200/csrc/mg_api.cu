@@ -614,7 +614,7 @@ extern "C" int mg_model_info(const mg_ctx *ctx, int *n_sv, double *gamma, double
 // ---------------------------------------------------------------------------
 // workspace
 // ---------------------------------------------------------------------------
-static const int64_t kMaxChunkRows = 1 << 21;  // 2 M candidates = 3.2 GB of feature rows in flight
+static const int64_t kMaxChunkRows = 1 << 22;  // 4 M candidates = 6.4 GB of feature rows in flight (one launch tail per chunk)
 
 static int ensure_x(mg_ctx *ctx, int64_t rows)
 {
