@@ -325,7 +325,6 @@ k_svr_fact(const DevFact *__restrict__ fc, const DevFTask *__restrict__ tasks, i
         for (int ch = 0; ch < n_chunks; ch++) {
             const int st = ch & 1;
             mbar_wait(&slab_full[st], (ch >> 1) & 1);
-            if (ch >= 2) mbar_wait(&e_empty[st], ((ch >> 1) & 1) ^ 1);
             const double *sb = slab + st * FACT_BLOB;
             const double *ws = wst + st * C;
             double *Eb = E + st * ESZ;
@@ -390,6 +389,9 @@ k_svr_fact(const DevFact *__restrict__ fc, const DevFTask *__restrict__ tasks, i
 #pragma unroll
                     for (int i = 0; i < 8; i++) t[i] *= ws[((i >> 1) & 1) * 8 + 2 * tig + (i & 1)];
                 }
+                // the table of chunk ch - 2 must have been gathered before it is overwritten: waiting here, not at the
+                // top of the chunk, lets the first unit's contraction and exp run beside the gather's tail
+                if (ui == 0 && ch >= 2) mbar_wait(&e_empty[st], ((ch >> 1) & 1) ^ 1);
 #pragma unroll
                 for (int i = 0; i < 8; i++)
                     Eb[(row0 + (i >> 2) * 8 + gid) * EST + ((i >> 1) & 1) * 8 + 2 * tig + (i & 1)] = t[i];
