@@ -108,9 +108,9 @@ __host__ __device__ inline uint32_t fd_pack(uint32_t kind, uint32_t part, uint32
 // factored SVR (k_svr_fact.cu): block sizes, padded strides, per-chunk blob layout
 // ---------------------------------------------------------------------------
 #define FACT_C 16          // support vectors per chunk
-#define FACT_MATH_WARPS 12
-#define FACT_GATHER_WARPS 4
-#define FACT_CPT 4                                      // candidates per gather thread
+#define FACT_MATH_WARPS 11
+#define FACT_GATHER_WARPS 5
+#define FACT_CPT 3                                      // candidates per gather thread
 #define FACT_THREADS ((FACT_MATH_WARPS + FACT_GATHER_WARPS) * 32)       // 16 warps: 128 registers per thread
 #define FACT_K_ARM 24      // 21 arm ratios + arm length + log copy, padded to a multiple of 4 (either role)
 #define FACT_K_INS 88      // 86 insert features
