@@ -345,11 +345,11 @@ k_svr_fact(const DevFact *__restrict__ fc, const DevFTask *__restrict__ tasks, i
                     F = FA + (m * 16) * FACT_LD_ARM; ld = FACT_LD_ARM; row0 = m * 16; is_lig = ligA;
                     S = sb + (is_lig ? FACT_OFF_LIG : FACT_OFF_EXT); ssb = sb + FACT_OFF_SS + (is_lig ? C : 0);
                 }
-                // 8 independent accumulator chains: 2 row fragments x 2 column fragments x even/odd k.  The even chains
-                // start from -gamma (||row||^2 + ||s||^2 [+ junction term]) (pre-scaled tables; the SV blocks carry the
-                // factor 2 gamma), so the contraction ends on the exponent itself.  One 16-byte load serves two k4 steps:
-                // thread-in-group t holds columns 8i+2t (even step) and 8i+2t+1 (odd step)
-                double a[2][2][2], b[2][2][2];
+                // 4 accumulator chains per warp (2 row fragments x 2 column fragments; the other warps of the scheduler
+                // keep the pipe fed).  They start from -gamma (||row||^2 + ||s||^2 [+ junction term]) (pre-scaled tables;
+                // the SV blocks carry the factor 2 gamma), so the contraction ends on the exponent itself.  One 16-byte
+                // load serves two k4 steps: thread-in-group t holds columns 8i+2t (even step) and 8i+2t+1 (odd step)
+                double a[2][2][2];
 #pragma unroll
                 for (int mf = 0; mf < 2; mf++) {
                     const int row = row0 + mf * 8 + gid;
@@ -359,7 +359,6 @@ k_svr_fact(const DevFact *__restrict__ fc, const DevFTask *__restrict__ tasks, i
                     for (int nf = 0; nf < 2; nf++) {
                         const double2 tv = *reinterpret_cast<const double2 *>(tb + nf * 8 + 2 * tig);
                         a[mf][nf][0] = xr + tv.x; a[mf][nf][1] = xr + tv.y;
-                        b[mf][nf][0] = b[mf][nf][1] = 0.0;
                     }
                 }
                 const double2 *f0 = reinterpret_cast<const double2 *>(F + gid * ld + 2 * tig);
@@ -375,15 +374,15 @@ k_svr_fact(const DevFact *__restrict__ fc, const DevFTask *__restrict__ tasks, i
                     dmma884(a[0][1][0], a[0][1][1], x0.x, p1.x);
                     dmma884(a[1][0][0], a[1][0][1], x1.x, p0.x);
                     dmma884(a[1][1][0], a[1][1][1], x1.x, p1.x);
-                    dmma884(b[0][0][0], b[0][0][1], x0.y, p0.y);
-                    dmma884(b[0][1][0], b[0][1][1], x0.y, p1.y);
-                    dmma884(b[1][0][0], b[1][0][1], x1.y, p0.y);
-                    dmma884(b[1][1][0], b[1][1][1], x1.y, p1.y);
+                    dmma884(a[0][0][0], a[0][0][1], x0.y, p0.y);
+                    dmma884(a[0][1][0], a[0][1][1], x0.y, p1.y);
+                    dmma884(a[1][0][0], a[1][0][1], x1.y, p0.y);
+                    dmma884(a[1][1][0], a[1][1][1], x1.y, p1.y);
                 }
                 // epilogue, stage by stage over the lane's 8 elements so that 8 exp chains are in flight
                 double t[8];
 #pragma unroll
-                for (int i = 0; i < 8; i++) t[i] = a[i >> 2][(i >> 1) & 1][i & 1] + b[i >> 2][(i >> 1) & 1][i & 1];
+                for (int i = 0; i < 8; i++) t[i] = a[i >> 2][(i >> 1) & 1][i & 1];
                 if (!(MG_FACT_ABLATE & 1)) expn_nonpos<8>(t, etab);
                 if (is_ins) {
 #pragma unroll
