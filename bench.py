@@ -165,9 +165,9 @@ def cpu_baseline(cfg, model_path, lrc_by_region, genome, budget_s=12.0, cores=No
 
 # ----------------------------------------------------------------------------------
 # FP64-pipe slots per exp epilogue element, counted as FMA = 2 flop each (DMMA and DFMA share one pipe on B200):
-# dense kernel 19 instructions (norm combine, clamp, scale, 11-instruction exp, alpha FMA); factored kernel 11
-# (accumulator start value, 10-instruction exp; its tables are pre-scaled by -gamma)
-EXP_FLOP_DENSE, EXP_FLOP_FACT = 38.0, 22.0
+# dense kernel 19 instructions (norm combine, clamp, scale, 11-instruction exp, alpha FMA); factored kernel 10
+# (the 10-instruction exp: the contraction itself ends on the exponent, its tables are pre-scaled by -gamma)
+EXP_FLOP_DENSE, EXP_FLOP_FACT = 38.0, 20.0
 
 
 def issued_fp64_flop(tm) -> float:

@@ -296,12 +296,15 @@ k_svr_fact(const DevFact *__restrict__ fc, const DevFTask *__restrict__ tasks, i
             // a non-finite feature (log10(0) = -inf copy) makes every kernel value of the row 0, as in libsvm:
             // park the row at exponent -inf with finite (zero) features so the contraction stays NaN free
             const bool finite = fabs(ssum) <= 1.7976931348623157e308;
+            // -gamma ||row||^2 rides in the block's spare column (the SV blocks hold 1 there), so the contraction adds it
+            const double nrm = finite ? -gamma * ssum : __longlong_as_double(0xfff0000000000000LL);
+            const int kstar = role[j] == 2 ? FACT_K_INS - 2 : FACT_K_ARM - 1;
 #pragma unroll
             for (int i = 0; i < 3; i++) {
                 const int k = i * 32 + lane;
-                if (k < ld[j]) dst[k] = finite ? v[j][i] : 0.0;
+                if (k < ld[j]) dst[k] = k == kstar ? nrm : (finite ? v[j][i] : 0.0);
             }
-            if (lane == 0) xx[row] = finite ? -gamma * ssum : __longlong_as_double(0xfff0000000000000LL);  // exponent scale
+            if (lane == 0) xx[row] = nrm;
             int code = 16;
             if (jv[j] == 1.0) code = lane;
 #pragma unroll
@@ -346,19 +349,19 @@ k_svr_fact(const DevFact *__restrict__ fc, const DevFTask *__restrict__ tasks, i
                     S = sb + (is_lig ? FACT_OFF_LIG : FACT_OFF_EXT); ssb = sb + FACT_OFF_SS + (is_lig ? C : 0);
                 }
                 // 4 accumulator chains per warp (2 row fragments x 2 column fragments; the other warps of the scheduler
-                // keep the pipe fed).  They start from -gamma (||row||^2 + ||s||^2 [+ junction term]) (pre-scaled tables;
-                // the SV blocks carry the factor 2 gamma), so the contraction ends on the exponent itself.  One 16-byte
+                // keep the pipe fed).  They start from -gamma (||s||^2 [+ junction term]) (pre-scaled tables), -gamma ||row||^2
+                // comes in through the spare column and the SV blocks carry the factor 2 gamma, so the contraction ends
+                // on the exponent itself.  One 16-byte
                 // load serves two k4 steps: thread-in-group t holds columns 8i+2t (even step) and 8i+2t+1 (odd step)
                 double a[2][2][2];
 #pragma unroll
                 for (int mf = 0; mf < 2; mf++) {
                     const int row = row0 + mf * 8 + gid;
-                    const double xr = xx[row];
                     const double *tb = is_lig ? sb + FACT_OFF_JT + jc[row] * C : ssb;
 #pragma unroll
                     for (int nf = 0; nf < 2; nf++) {
                         const double2 tv = *reinterpret_cast<const double2 *>(tb + nf * 8 + 2 * tig);
-                        a[mf][nf][0] = xr + tv.x; a[mf][nf][1] = xr + tv.y;
+                        a[mf][nf][0] = tv.x; a[mf][nf][1] = tv.y;
                     }
                 }
                 const double2 *f0 = reinterpret_cast<const double2 *>(F + gid * ld + 2 * tig);

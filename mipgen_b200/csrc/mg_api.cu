@@ -503,6 +503,10 @@ static int upload_model(mg_ctx *ctx, const std::vector<double> &dense, const std
             for (int k = 0; k < 16; k++) b[FACT_OFF_JT + k * FACT_C + r] = -gamma * (sl + (1.0 - 2.0 * srow[174 + k]));
             b[FACT_OFF_JT + 16 * FACT_C + r] = -gamma * sl;
             for (int k = 0; k < 86; k++) { b[FACT_OFF_INS + r * FACT_LD_INS + k] = g2 * srow[66 + k]; si += srow[66 + k] * srow[66 + k]; }
+            // spare columns: the rows carry -gamma ||row||^2 there (k_svr_fact phase 1)
+            b[FACT_OFF_EXT + r * FACT_LD_ARM + FACT_K_ARM - 1] = 1.0;
+            b[FACT_OFF_LIG + r * FACT_LD_ARM + FACT_K_ARM - 1] = 1.0;
+            b[FACT_OFF_INS + r * FACT_LD_INS + FACT_K_INS - 2] = 1.0;
             b[FACT_OFF_SS + r] = -gamma * se; b[FACT_OFF_SS + FACT_C + r] = -gamma * sl; b[FACT_OFF_SS + 2 * FACT_C + r] = -gamma * si;
         }
         CUDA_TRY(ctx, cudaMalloc(&ctx->d_fact_blob, blob.size() * 8));
