@@ -20,10 +20,11 @@
 //      epilogue and parks them in three small shared-memory tables;
 //   2. gives every candidate one thread that adds  sum_i  E_a[ra][i] * E_q[rq][i] * E_ins'[ri][i]
 //      to its running score (E_ins' already carries alpha_i * exp(-g d_lrc(region, i))).
-// Same FP64 arithmetic as the dense kernel per block (||x||^2 + ||s||^2 - 2 x.s), ~1e-13 relative
-// agreement with libsvm; work per (candidate, SV) drops from ~219 to ~45 FP64-pipe slots.
+// Same FP64 arithmetic as the dense kernel per block (||x||^2 + ||s||^2 - 2 x.s, here scaled by -gamma at
+// model upload so that the contraction ends on the exponent), ~1e-13 relative agreement with libsvm;
+// work per (candidate, SV) drops from ~219 to ~35 FP64-pipe slots.
 // Row features are read from the feature rows K-feat wrote (a representative candidate per row).
-// SV blocks are re-tiled at model upload: one 21 KB bulk copy (cp.async.bulk / mbarrier) per chunk.
+// SV blocks are re-tiled at model upload: one 20 KB bulk copy (cp.async.bulk / mbarrier) per chunk.
 #include "mg_common.cuh"
 
 namespace {
@@ -132,8 +133,10 @@ __device__ __forceinline__ void mbar_arrive(uint64_t *bar)
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 
-// Warp roles: warps [0, kMathWarps) build the factor tables of chunk c+1 on the FP64 pipe while
-// warps [kMathWarps, 2 kMathWarps) gather chunk c through the LSU; one more warp feeds the SV blobs.
+// Warp roles: warps [0, kMathWarps) build the factor tables of chunk c+1 on the FP64 pipe while warps
+// [kMathWarps, kMathWarps + kGatherWarps) gather chunk c through the LSU; the first gather thread also
+// fetches the SV blobs.  11 + 5 warps: the default configuration has 19 work units per chunk (3 insert,
+// 16 arm), which balance over 11 warps, and the gather is co-critical.
 constexpr int kMathWarps = FACT_MATH_WARPS, kGatherWarps = FACT_GATHER_WARPS, kGatherThreads = kGatherWarps * 32, kCpt = FACT_CPT;
 constexpr int kUnitsPerWarp = 24;
 
