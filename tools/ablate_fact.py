@@ -2,11 +2,12 @@
 """Where does the factored K-svr spend its time?  Runs the bench panel through library variants built with
 -DMG_FACT_ABLATE=<mask> (parts of the kernel removed; results are wrong, only the timing is meaningful):
 
-    for v in 0 1 2 4 8 16 31; do nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -shared \
+    for v in 0 1 2 4 8 15; do nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -shared \
         -Xcompiler -fPIC -DMG_FACT_ABLATE=$v -o tools/_bin/libmg_ablate_$v.so mipgen_b200/csrc/*.cu; done
     gpurun -- python tools/ablate_fact.py
 
-mask bits: 1 no exp, 2 no insert-block DMMA, 4 no gather arithmetic, 8 no arm DMMA, 16 no epilogue.
+mask bits: 1 no exp, 2 no insert-block DMMA, 4 no gather arithmetic (and loads), 8 no arm DMMA.
+The additive picture these timings give, and the restructurings they led to, are in DESIGN.md section 6.
 """
 import glob
 import os
