@@ -185,6 +185,18 @@ def universal_middle(lig_tag_length: int = 0, ext_tag_length: int = 5) -> str:
     return "N" * lig_tag_length + UNIVERSAL_CONSTANT + "N" * ext_tag_length
 
 
+def describe_candidates(cfg: Config, r: Region, idx: np.ndarray):
+    """Geometry and arm copy numbers of region r's candidates idx (mg_describe_candidates; no device needed).
+    Returns a list of dicts with the fields of mg_mip_info."""
+    c, _k = _c_config(cfg)
+    arr, _k2 = _c_regions([r])
+    idx = np.ascontiguousarray(idx, np.int64)
+    info = (MgMipInfo * max(1, idx.size))()
+    if load_library().mg_describe_candidates(C.byref(c), arr, _ptr(idx, c_int64_p), idx.size, info) != 0:
+        raise MgError("mg_describe_candidates: bad config or grid index")
+    return [{n: getattr(info[k], n) for n, _t in MgMipInfo._fields_} for k in range(idx.size)]
+
+
 def design_records(cfg: Config, r: Region, idx: np.ndarray, score: np.ndarray, chrom: str, label: str, feature_start: int,
                    feature_stop: int, first_index: int, middle: Optional[str] = None, raw: bool = False):
     """The all_mips.txt / collapsed_mips.txt lines of region r's candidates idx (grid indices, in output order),

@@ -79,6 +79,45 @@ def test_records_from_oracle_scores_equal_reference_files(oracle, case):
     assert file_digest(col_txt) == g["collapsed_mips"], "collapsed_mips.txt differs from the reference CLI's file"
 
 
+def test_describe_candidates_geometry_copies_and_errors(oracle):
+    """mg_describe_candidates: Plus/Minus geometry (PlusSVMipv4.cpp:7-14, MinusSVMipv4.cpp:30-37), arm copy numbers
+    from the per-oligo-size table (mipgen.cpp:612-613, absent key = 0), and its error path."""
+    cfg = sp.small_config((40, 43, 45), 162, 152, 5)
+    _genome, regions = sp.inputs(oracle, cfg)
+    r = regions[0]
+    rng = np.random.default_rng(5)
+    r.copies = rng.integers(0, 200, size=(len(cfg.oligo_sizes), len(r.seq))).astype(np.int32)
+    n = cfg.grid_size(r)
+    idx = rng.choice(n, 500, replace=False).astype(np.int64)
+    s0 = cfg.first_scan_start(r)
+    for i, m in zip(idx, mg.describe_candidates(cfg, r, idx)):
+        strand, q = int(i) & 1, int(i) >> 1
+        p, q = q % cfg.n_pairs, q // cfg.n_pairs
+        ci, si = q % len(cfg.captures), q // len(cfg.captures)
+        e, l = cfg.ext_len[p], cfg.lig_len[p]
+        s = s0 + si
+        t = s + cfg.captures[ci] - e - l - 1
+        want = dict(strand=strand, ext_len=e, lig_len=l, scan_start=s, scan_stop=t)
+        if strand == 0:
+            want.update(ext_start=s - e, ext_stop=s - 1, lig_start=t + 1, lig_stop=t + l)
+        else:
+            want.update(lig_start=s - l, lig_stop=s - 1, ext_start=t + 1, ext_stop=t + e)
+
+        def copy(start, length):
+            k = cfg.oligo_sizes.index(length)
+            a = start - r.seq_start
+            return int(r.copies[k, a]) if 0 <= a < len(r.seq) else 0
+
+        want.update(ext_copy=copy(want["ext_start"], e), lig_copy=copy(want["lig_start"], l))
+        assert m == want
+    r.copies = None
+    assert all(m["ext_copy"] == 1 and m["lig_copy"] == 1 for m in mg.describe_candidates(cfg, r, idx[:5]))
+    with pytest.raises(mg.MgError):
+        mg.describe_candidates(cfg, r, np.array([n], np.int64))
+    with pytest.raises(mg.MgError):
+        mg.describe_candidates(cfg, r, np.array([-1], np.int64))
+
+
 @pytest.mark.gpu
 @pytest.mark.parametrize("case", sorted(sp.CASES))
 def test_records_from_device_scores_equal_reference_files(oracle, case):
