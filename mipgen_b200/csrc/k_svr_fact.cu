@@ -372,9 +372,7 @@ k_svr_fact(const DevFact *__restrict__ fc, const DevFTask *__restrict__ tasks, i
                 const double2 *s0 = reinterpret_cast<const double2 *>(S + gid * ld + 2 * tig);
                 const double2 *s1 = reinterpret_cast<const double2 *>(S + (8 + gid) * ld + 2 * tig);
                 const bool skip = ((MG_FACT_ABLATE & 2) && is_ins) || ((MG_FACT_ABLATE & 8) && !is_ins);
-#pragma unroll 3
-                for (int it = 0; it < ld / 8; it++) {
-                    if (skip) break;
+                auto dmma_iter = [&](int it) {
                     const double2 x0 = f0[it * 4], x1 = f1[it * 4], p0 = s0[it * 4], p1 = s1[it * 4];
                     dmma884(a[0][0][0], a[0][0][1], x0.x, p0.x);
                     dmma884(a[0][1][0], a[0][1][1], x0.x, p1.x);
@@ -384,6 +382,17 @@ k_svr_fact(const DevFact *__restrict__ fc, const DevFTask *__restrict__ tasks, i
                     dmma884(a[0][1][0], a[0][1][1], x0.y, p1.y);
                     dmma884(a[1][0][0], a[1][0][1], x1.y, p0.y);
                     dmma884(a[1][1][0], a[1][1][1], x1.y, p1.y);
+                };
+                // both trip counts are compile-time constants: fully unrolled, the fragment loads of later iterations
+                // are issued under the DMMAs of earlier ones
+                if (!skip) {
+                    if (is_ins) {
+#pragma unroll
+                        for (int it = 0; it < FACT_LD_INS / 8; it++) dmma_iter(it);
+                    } else {
+#pragma unroll
+                        for (int it = 0; it < FACT_LD_ARM / 8; it++) dmma_iter(it);
+                    }
                 }
                 // epilogue, stage by stage over the lane's 8 elements so that 8 exp chains are in flight
                 double t[8];
