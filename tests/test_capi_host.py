@@ -84,6 +84,42 @@ def test_tile_replay_matches_oracle_on_synthetic_scores():
     assert fired > 10
 
 
+def test_tile_replay_and_grid_geometry_on_random_configs():
+    """Random capture ranges / increments / arm-sum sets and regions hard against the chromosome start:
+    grid size, enumeration replay and candidate geometry of the host helpers agree with the oracle."""
+    o = Oracle()
+    rng = np.random.default_rng(2024)
+    all_sums = list(range(36, 50))
+    for trial in range(12):
+        sums = tuple(sorted(rng.choice(all_sums, int(rng.integers(1, 4)), replace=False).tolist()))
+        max_cap = int(rng.integers(120, 260))
+        min_cap = int(max(max(sums) + 1, max_cap - rng.integers(0, 40)))
+        inc = int(rng.choice([0, 1, 3, 5, 7]))
+        cfg = small_config(sums, max_cap, min_cap, inc)
+        genome, regs = synthetic_regions(o, cfg, 2, 5, 120, 300 + trial, with_lrc=False)
+        regs.append(panel.cut_region(genome, int(rng.integers(20, 60)), int(rng.integers(70, 140)), cfg))
+        for r in regs:
+            v, _l, _s, _f = o.grid_region(r, cfg, None)
+            assert mg.config_grid_size(cfg, r) == v.size == cfg.grid_size(r)
+            if v.size == 0:
+                continue
+            score = rng.uniform(0.3, 1.02, v.size)
+            score[rng.random(v.size) < 0.03] = -1000.0
+            score[~v.astype(bool)] = np.nan
+            for method, upper in ((0, 0.98), (1, 0.9), (2, 0.98)):
+                a = mg.tile_replay(cfg, r, v, score, method, True, upper)
+                b = o.tile_replay(r, cfg, v, score, method, True, upper)
+                assert np.array_equal(a, b), (trial, sums, max_cap, min_cap, inc, method)
+            # geometry of a few enumerated candidates: every arm and the target lie inside the region's sequence
+            idx = a[:: max(1, a.size // 50)]
+            for m in mg.describe_candidates(cfg, r, idx):
+                lo = min(m["ext_start"], m["lig_start"])
+                hi = max(m["ext_stop"], m["lig_stop"])
+                assert r.seq_start <= lo and hi <= r.seq_stop
+                assert m["scan_stop"] - m["scan_start"] + 1 + m["ext_len"] + m["lig_len"] in cfg.captures
+                assert m["ext_stop"] - m["ext_start"] + 1 == m["ext_len"] and m["lig_stop"] - m["lig_start"] + 1 == m["lig_len"]
+
+
 def test_lpt_sharding_is_a_partition_and_balanced():
     rng = np.random.default_rng(1)
     costs = rng.integers(100, 100000, 61).tolist()
