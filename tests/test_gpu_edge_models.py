@@ -70,3 +70,37 @@ def test_config_outside_the_factored_tables_falls_back_to_dense(ctx, oracle):
     with pytest.raises(mg.MgError):
         ctx.score_regions(regions, mg.MG_WANT_SVR)
     ctx.set_svr_mode(0)
+
+
+def test_random_configs_match_oracle(ctx, oracle):
+    """Random capture ranges / increments / arm-sum sets (incl. increments that do not divide the range and a
+    region clamped at the chromosome start): validity and features bit-exact, scores within tolerance."""
+    rng = np.random.default_rng(77)
+    all_sums = list(range(36, 50))
+    for trial in range(6):
+        sums = tuple(sorted(rng.choice(all_sums, int(rng.integers(1, 4)), replace=False).tolist()))
+        max_cap = int(rng.integers(120, 260))
+        min_cap = int(max(max(sums) + 1, max_cap - rng.integers(0, 30)))
+        inc = int(rng.choice([0, 1, 3, 5, 7]))
+        cfg = small_config(sums, max_cap, min_cap, inc)
+        genome, regions = synthetic_regions(oracle, cfg, 2, 5, 40, 600 + trial)
+        edge = panel.cut_region(genome, int(rng.integers(20, 60)), int(rng.integers(70, 110)), cfg, 0, "edge")
+        edge.lrc = rng.uniform(0, 0.3, 44)
+        regions.append(edge)
+        model = random_model(oracle, cfg, 20, 900 + trial, os.path.join(tmpdir(), "m.model"))
+        ctx.set_config(cfg)
+        ctx.load_svr_model(model)
+        offs, valid, lo, sv, ft = ctx.score_regions(regions, mg.MG_WANT_LOGISTIC | mg.MG_WANT_SVR | mg.MG_WANT_FEATURES)
+        _o, valid2, _l, sv2, _f = ctx.score_regions(regions, mg.MG_WANT_SVR)  # workspace path (factored kernel when it fits)
+        h = oracle.svm_load_model(model)
+        for i, r in enumerate(regions):
+            a, b = offs[i], offs[i + 1]
+            wv, wl, ws, wf = oracle.grid_region(r, cfg, h, want_logistic=True, want_svr=True, want_feats=True)
+            tag = (trial, sums, max_cap, min_cap, inc, i)
+            assert b - a == wv.size, tag
+            assert np.array_equal(valid[a:b], wv) and np.array_equal(valid2[a:b], wv), tag
+            ok = wv.astype(bool)
+            assert np.array_equal(ft[a:b][ok], wf[ok]), tag
+            assert rel_err(lo[a:b], wl) <= 1e-12, tag
+            assert rel_err(sv[a:b], ws) <= SVR_RTOL and rel_err(sv2[a:b], ws) <= SVR_RTOL, tag
+        oracle.svm_free(h)
