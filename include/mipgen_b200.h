@@ -80,6 +80,15 @@ typedef struct {
                           mipgen.cpp:83, 612-613; 0 = absent key); NULL => every copy is 1   */
     int scan_begin;    /* optional explicit range of scan starts [scan_begin, scan_end];      */
     int scan_end;      /*   both 0 => the reference's rule (mipgen.cpp:421-425)               */
+    /* Selection-only inputs (they change no score, only condense/collapse): NULL = absent.              */
+    const char *masked_seq;     /* masked_chromosomal_sequence (TRF output, mipgen.cpp:1045-1084): seq_len
+                                   characters, 'N' = masked (mipgen.cpp:606-610); NULL => seq itself,
+                                   which is what the reference uses with -trf off (mipgen.cpp:1058-1062) */
+    const uint8_t *snp;         /* [seq_len] non-zero where chr_snp_positions holds seq_start + i
+                                   (mipgen.cpp:634-636, 698-700): feeds snp_count                        */
+    const uint8_t *unmappable;  /* [n_capture_sizes][seq_len], capture index as in the grid: non-zero where
+                                   unmappable_positions[capture][chr] holds seq_start + i as a MIP start
+                                   (mipgen.cpp:615-625); NULL also stands for -check_copy_number off     */
 } mg_region;
 
 /* One SVMipv4 object as mipgen.cpp leaves it after design_mip: strand-oriented strings
@@ -183,7 +192,8 @@ int mg_panel_device_ptrs(const mg_panel *p, const uint8_t **valid, const double 
 /* condense_mips (mipgen.cpp:1670-1746, on top of the tile loop's score-dependent enumeration,
  * mipgen.cpp:426-497) and collapse_mips (mipgen.cpp:1617-1649) over a scored panel: the best candidate
  * per (scan start, strand) and per (position, strand), as global grid indices of the panel (-1: none).
- * Without TRF masking, SNP data and mapping failures (the defaults); arm copies from the copy tables. */
+ * Arm copies come from the copy tables; arm_fraction_masked, snp_count and mapping_failed (mipgen.cpp:606-625,
+ * 634-760) from the regions' masked_seq / snp / unmappable inputs. */
 typedef struct {
     int method;                 /* 0 logistic, 1 svr, 2 mixed (tile phase = logistic scores)              */
     int heuristic;              /* -logistic_heuristic != "off"                                          */
@@ -191,6 +201,7 @@ typedef struct {
     double upper_score_limit;   /* -{svr,logistic}_optimal_score                                         */
     int max_arm_copy;           /* -max_arm_copy_product (75)                                            */
     int target_arm_copy;        /* -target_arm_copy (20)                                                 */
+    double masked_arm_threshold;/* -masked_arm_threshold (0.5): mipgen.cpp:1629, 1701                        */
 } mg_select_params;
 /* number of scan starts / coverable positions of a region (positions: first scan start ..
  * stop_flanked + max_capture - min arm sum - 1) */
@@ -243,6 +254,45 @@ int64_t mg_format_mip_record(const mg_region *r, const mg_mip_info *m, double sc
 int64_t mg_format_mip_records(const mg_config *cfg, const mg_region *r, const int64_t *idx, int n, const double *score,
                               const char *chr, const char *label, int feature_start, int feature_stop,
                               const char *universal_middle, int first_index, char *buf, int64_t cap);
+
+/* ---- one call per batch of Featurev5 objects: what tile_regions does per feature up to collapse_mips ----------
+ * (mipgen.cpp:412-505: the candidate loop nest, condense_mips, collapse_mips), for a caller that keeps pick_mips
+ * (mipgen.cpp:1506-1614) on the host.  Regions are walked in sub-batches of at most max_batch_candidates grid
+ * points (0 = a default of 2^26), so device memory stays bounded however long the region list is; only the
+ * winners (and, if asked for, the full grids) come back.  Indices are LOCAL to each region's grid
+ * (mg_describe_candidates / mg_format_mip_records take them as they are), -1 = none. */
+typedef struct {
+    int64_t *scan_best;          /* [2 * scan_off[n]]  scan_strand_best_mip: entry (scan_off[i] + scan_idx)*2 + strand   */
+    int64_t *pos_best;           /* [2 * pos_off[n]]   pos_strand_best_mip:  entry (pos_off[i] + pos_idx)*2 + strand     */
+    double *scan_best_logistic;  /* [2 * scan_off[n]]  logistic score of each scan_best winner (NaN where -1); or NULL   */
+    double *scan_best_svr;       /* [2 * scan_off[n]]  SVR score of each scan_best winner; or NULL                       */
+    uint8_t *valid;              /* [grid_off[n]] full grids in region order; each may be NULL                           */
+    double *logistic;
+    double *svr;
+} mg_tile_result;
+/* Prefix sums a caller needs to size mg_tile_result (pure host arithmetic): grid points, scan starts and coverable
+ * positions of regions[0..n); each array has n + 1 entries and may be NULL. */
+int mg_tile_sizes(const mg_config *cfg, const mg_region *regions, int n, int64_t *grid_off, int64_t *scan_off, int64_t *pos_off);
+/* want: MG_WANT_LOGISTIC and/or MG_WANT_SVR (what to score); sp selects on sp->method's scores (mixed = logistic,
+ * mipgen.cpp:467-468) and may be NULL (score only: scan_best / pos_best are not written). */
+int mg_tile_regions(mg_ctx *ctx, const mg_region *regions, int n, int want, const mg_select_params *sp,
+                    int64_t max_batch_candidates, mg_tile_result *out);
+
+/* ---- the same over several GPUs of one box ---------------------------------------------------------
+ * Regions are independent (mipgen.cpp:412-525), so they are partitioned over the contexts by longest-processing-time
+ * on their grid sizes; every context runs on its own host thread, stream and device and writes its regions' slices
+ * of the caller's arrays, which therefore come back in the caller's region order.  No collective, no NCCL.  All
+ * contexts must carry the same config and model.  Returns the first error of any context. */
+int mg_tile_regions_multi(mg_ctx *const *ctxs, int n_ctx, const mg_region *regions, int n, int want, const mg_select_params *sp,
+                          int64_t max_batch_candidates, mg_tile_result *out);
+/* mg_score_regions over several GPUs: out_offsets[n+1] (may be NULL), valid / logistic / svr as in mg_score_regions. */
+int mg_score_regions_multi(mg_ctx *const *ctxs, int n_ctx, const mg_region *regions, int n, int want, int64_t *out_offsets,
+                           uint8_t *valid, double *logistic, double *svr);
+/* the partition both calls use: owner[i] = index of the context that scores region i */
+int mg_partition_regions(const mg_config *cfg, const mg_region *regions, int n, int n_parts, int *owner);
+
+/* scores of n grid points of a scored panel (panel-global indices; -1 yields NaN); logistic / svr may be NULL */
+int mg_panel_gather(mg_ctx *ctx, mg_panel *p, const int64_t *idx, int64_t n, double *logistic, double *svr);
 
 #ifdef __cplusplus
 }

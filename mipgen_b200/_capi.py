@@ -33,7 +33,8 @@ class MgConfig(C.Structure):
 class MgRegion(C.Structure):
     _fields_ = [("seq", C.c_char_p), ("seq_len", C.c_int), ("seq_start", C.c_int), ("seq_stop", C.c_int),
                 ("start_flanked", C.c_int), ("stop_flanked", C.c_int), ("lrc", c_double_p),
-                ("copies", c_int_p), ("scan_begin", C.c_int), ("scan_end", C.c_int)]
+                ("copies", c_int_p), ("scan_begin", C.c_int), ("scan_end", C.c_int),
+                ("masked_seq", C.c_char_p), ("snp", c_ubyte_p), ("unmappable", c_ubyte_p)]
 
 
 class MgCandidate(C.Structure):
@@ -44,7 +45,13 @@ class MgCandidate(C.Structure):
 
 class MgSelectParams(C.Structure):
     _fields_ = [("method", C.c_int), ("heuristic", C.c_int), ("lower_score_limit", C.c_double),
-                ("upper_score_limit", C.c_double), ("max_arm_copy", C.c_int), ("target_arm_copy", C.c_int)]
+                ("upper_score_limit", C.c_double), ("max_arm_copy", C.c_int), ("target_arm_copy", C.c_int),
+                ("masked_arm_threshold", C.c_double)]
+
+
+class MgTileResult(C.Structure):
+    _fields_ = [("scan_best", c_int64_p), ("pos_best", c_int64_p), ("scan_best_logistic", c_double_p),
+                ("scan_best_svr", c_double_p), ("valid", c_ubyte_p), ("logistic", c_double_p), ("svr", c_double_p)]
 
 
 class MgMipInfo(C.Structure):
@@ -104,6 +111,15 @@ SYMBOLS = [
                                           C.c_char_p, C.c_int, C.c_int, C.c_char_p, C.c_int, C.c_char_p, C.c_int64]),
     ("mg_format_mip_record", C.c_int64, [C.POINTER(MgRegion), C.POINTER(MgMipInfo), C.c_double, C.c_char_p, C.c_char_p, C.c_int,
                                          C.c_int, C.c_char_p, C.c_int, C.c_char_p, C.c_int64]),
+    ("mg_tile_sizes", C.c_int, [C.POINTER(MgConfig), C.POINTER(MgRegion), C.c_int, c_int64_p, c_int64_p, c_int64_p]),
+    ("mg_tile_regions", C.c_int, [C.c_void_p, C.POINTER(MgRegion), C.c_int, C.c_int, C.POINTER(MgSelectParams), C.c_int64,
+                                  C.POINTER(MgTileResult)]),
+    ("mg_tile_regions_multi", C.c_int, [C.POINTER(C.c_void_p), C.c_int, C.POINTER(MgRegion), C.c_int, C.c_int,
+                                        C.POINTER(MgSelectParams), C.c_int64, C.POINTER(MgTileResult)]),
+    ("mg_score_regions_multi", C.c_int, [C.POINTER(C.c_void_p), C.c_int, C.POINTER(MgRegion), C.c_int, C.c_int, c_int64_p,
+                                         c_ubyte_p, c_double_p, c_double_p]),
+    ("mg_partition_regions", C.c_int, [C.POINTER(MgConfig), C.POINTER(MgRegion), C.c_int, C.c_int, c_int_p]),
+    ("mg_panel_gather", C.c_int, [C.c_void_p, C.c_void_p, c_int64_p, C.c_int64, c_double_p, c_double_p]),
 ]
 
 _lib = None
@@ -149,10 +165,83 @@ def _c_regions(regions: Sequence[Region]):
     for i, r in enumerate(regions):
         lrc = np.ascontiguousarray(r.lrc, np.float64) if r.lrc is not None else None
         cop = np.ascontiguousarray(r.copies, np.int32) if r.copies is not None else None
-        keep += [lrc, cop, r.seq]
+        snp = np.ascontiguousarray(r.snp, np.uint8) if getattr(r, "snp", None) is not None else None
+        unm = np.ascontiguousarray(r.unmappable, np.uint8) if getattr(r, "unmappable", None) is not None else None
+        msk = getattr(r, "masked_seq", None)
+        if msk is not None and len(msk) != len(r.seq):
+            raise ValueError("masked_seq must be as long as seq")
+        if snp is not None and snp.size != len(r.seq):
+            raise ValueError("snp must have one entry per base of seq")
+        keep += [lrc, cop, r.seq, snp, unm, msk]
         arr[i] = MgRegion(r.seq, len(r.seq), r.seq_start, r.seq_stop, r.start_flanked, r.stop_flanked,
-                          _ptr(lrc, c_double_p), _ptr(cop, c_int_p), getattr(r, "scan_begin", 0), getattr(r, "scan_end", 0))
+                          _ptr(lrc, c_double_p), _ptr(cop, c_int_p), getattr(r, "scan_begin", 0), getattr(r, "scan_end", 0),
+                          msk, _ptr(snp, c_ubyte_p), _ptr(unm, c_ubyte_p))
     return arr, keep
+
+
+def tile_sizes(cfg: Config, regions: Sequence[Region]):
+    """Prefix sums of grid points, scan starts and coverable positions over the regions (mg_tile_sizes; no device)."""
+    c, _k = _c_config(cfg)
+    arr, _k2 = _c_regions(regions)
+    n = len(regions)
+    g, s, p = (np.zeros(n + 1, np.int64) for _ in range(3))
+    if load_library().mg_tile_sizes(C.byref(c), arr, n, _ptr(g, c_int64_p), _ptr(s, c_int64_p), _ptr(p, c_int64_p)) != 0:
+        raise MgError("mg_tile_sizes: bad config")
+    return g, s, p
+
+
+def partition_regions(cfg: Config, regions: Sequence[Region], n_parts: int) -> np.ndarray:
+    """owner[i] = which of n_parts contexts scores region i (mg_partition_regions: LPT on grid sizes; no device)."""
+    c, _k = _c_config(cfg)
+    arr, _k2 = _c_regions(regions)
+    owner = np.zeros(max(1, len(regions)), np.int32)
+    if load_library().mg_partition_regions(C.byref(c), arr, len(regions), n_parts, _ptr(owner, c_int_p)) != 0:
+        raise MgError("mg_partition_regions: bad arguments")
+    return owner[:len(regions)]
+
+
+class TileResult:
+    """Outputs of mg_tile_regions[_multi] (numpy views over the caller-owned buffers)."""
+
+    def __init__(self, grid_off, scan_off, pos_off, scan_best, pos_best, scan_best_logistic, scan_best_svr, valid, logistic, svr):
+        self.grid_off, self.scan_off, self.pos_off = grid_off, scan_off, pos_off
+        self.scan_best, self.pos_best = scan_best, pos_best
+        self.scan_best_logistic, self.scan_best_svr = scan_best_logistic, scan_best_svr
+        self.valid, self.logistic, self.svr = valid, logistic, svr
+
+
+def tile_regions(ctxs, regions: Sequence[Region], want: int, select=None, full_grids: bool = False,
+                 max_batch_candidates: int = 0) -> TileResult:
+    """mg_tile_regions (one Context) / mg_tile_regions_multi (a list of Contexts on different GPUs).
+    select: None or dict(method, lower, upper, heuristic=True, max_arm_copy=75, target_arm_copy=20, masked_arm_threshold=0.5)."""
+    multi = isinstance(ctxs, (list, tuple))
+    first = ctxs[0] if multi else ctxs
+    g, s, p = tile_sizes(first.cfg, regions)
+    arr, _keep = _c_regions(regions)
+    ns, npos, ng = int(s[-1]), int(p[-1]), int(g[-1])
+    sb = np.full((ns, 2), -1, np.int64) if select else None
+    pb = np.full((npos, 2), -1, np.int64) if select else None
+    sbl = np.full((ns, 2), np.nan) if select and want & MG_WANT_LOGISTIC else None
+    sbs = np.full((ns, 2), np.nan) if select and want & MG_WANT_SVR else None
+    v = np.empty(ng, np.uint8) if full_grids else None
+    lo = np.empty(ng, np.float64) if full_grids and want & MG_WANT_LOGISTIC else None
+    sv = np.empty(ng, np.float64) if full_grids and want & MG_WANT_SVR else None
+    res = MgTileResult(_ptr(sb, c_int64_p), _ptr(pb, c_int64_p), _ptr(sbl, c_double_p), _ptr(sbs, c_double_p),
+                       _ptr(v, c_ubyte_p), _ptr(lo, c_double_p), _ptr(sv, c_double_p))
+    sp = None
+    if select:
+        sp = MgSelectParams(select["method"], int(select.get("heuristic", True)), select["lower"], select["upper"],
+                            select.get("max_arm_copy", 75), select.get("target_arm_copy", 20), select.get("masked_arm_threshold", 0.5))
+    spp = C.byref(sp) if sp is not None else None
+    lib = first.lib
+    if multi:
+        hs = (C.c_void_p * len(ctxs))(*[c.h for c in ctxs])
+        rc = lib.mg_tile_regions_multi(hs, len(ctxs), arr, len(regions), want, spp, max_batch_candidates, C.byref(res))
+        if rc != 0:
+            raise MgError("mg_tile_regions_multi failed (%d): %s" % (rc, "; ".join(lib.mg_last_error(c.h).decode() for c in ctxs)))
+    else:
+        first._check(lib.mg_tile_regions(first.h, arr, len(regions), want, spp, max_batch_candidates, C.byref(res)))
+    return TileResult(g, s, p, sb, pb, sbl, sbs, v, lo, sv)
 
 
 def config_grid_size(cfg: Config, r: Region) -> int:
@@ -248,8 +337,17 @@ class Panel:
         self.ctx._check(self.ctx.lib.mg_panel_fetch(self.ctx.h, self.h, _ptr(valid, c_ubyte_p), _ptr(logistic, c_double_p),
                                                     _ptr(svr, c_double_p), c_double_p()))
 
+    def gather(self, idx: np.ndarray, logistic: bool = False, svr: bool = False):
+        """Scores of the given panel-global grid indices (mg_panel_gather); -1 yields NaN."""
+        idx = np.ascontiguousarray(idx, np.int64).reshape(-1)
+        lo = np.empty(idx.size) if logistic else None
+        sv = np.empty(idx.size) if svr else None
+        self.ctx._check(self.ctx.lib.mg_panel_gather(self.ctx.h, self.h, _ptr(idx, c_int64_p), idx.size, _ptr(lo, c_double_p),
+                                                     _ptr(sv, c_double_p)))
+        return lo, sv
+
     def select(self, regions: Sequence[Region], method: int, lower: float, upper: float, heuristic: bool = True,
-               max_arm_copy: int = 75, target_arm_copy: int = 20):
+               max_arm_copy: int = 75, target_arm_copy: int = 20, masked_arm_threshold: float = 0.5):
         """condense_mips + collapse_mips on the device.  Returns (scan_offsets, scan_best[n,2], pos_offsets,
         pos_best[m,2]); entries are global grid indices of the panel or -1."""
         arr, _keep = _c_regions(regions)
@@ -261,7 +359,7 @@ class Panel:
             po[i + 1] = po[i] + self.ctx.lib.mg_region_position_count(self.ctx.h, C.byref(arr[i]))
         sb = np.empty((int(so[-1]), 2), np.int64)
         pb = np.empty((int(po[-1]), 2), np.int64)
-        sp = MgSelectParams(method, int(heuristic), lower, upper, max_arm_copy, target_arm_copy)
+        sp = MgSelectParams(method, int(heuristic), lower, upper, max_arm_copy, target_arm_copy, masked_arm_threshold)
         self.ctx._check(self.ctx.lib.mg_panel_select(self.ctx.h, self.h, C.byref(sp), _ptr(sb, c_int64_p), _ptr(pb, c_int64_p)))
         return so, sb, po, pb
 
@@ -389,6 +487,26 @@ class Context:
     def grid_size(self, r: Region) -> int:
         arr, _keep = self._regions([r])
         return int(self.lib.mg_grid_size(self.h, arr))
+
+    def score_regions_multi(self, others: Sequence["Context"], regions: Sequence[Region], want: int, out=None):
+        """mg_score_regions_multi over this context and `others` (one per GPU).  Returns offsets, valid, logistic, svr."""
+        ctxs = [self] + list(others)
+        g, _s, _p = tile_sizes(self.cfg, regions)
+        arr, _keep = self._regions(regions)
+        total = int(g[-1])
+        if out is not None:
+            valid, lo, sv = out
+        else:
+            valid = np.empty(total, np.uint8)
+            lo = np.empty(total, np.float64) if want & MG_WANT_LOGISTIC else None
+            sv = np.empty(total, np.float64) if want & MG_WANT_SVR else None
+        offsets = np.zeros(len(regions) + 1, np.int64)
+        hs = (C.c_void_p * len(ctxs))(*[c.h for c in ctxs])
+        rc = self.lib.mg_score_regions_multi(hs, len(ctxs), arr, len(regions), want, _ptr(offsets, c_int64_p), _ptr(valid, c_ubyte_p),
+                                             _ptr(lo, c_double_p), _ptr(sv, c_double_p))
+        if rc != 0:
+            raise MgError("mg_score_regions_multi failed (%d): %s" % (rc, "; ".join(self.lib.mg_last_error(c.h).decode() for c in ctxs)))
+        return offsets, valid, lo, sv
 
     def score_regions(self, regions: Sequence[Region], want: int = MG_WANT_LOGISTIC, out=None):
         """Host-buffer call (H2D + kernels + D2H inside).  Returns offsets, valid, logistic, svr, features."""

@@ -143,7 +143,8 @@ constexpr int kUnitsPerWarp = 24;
 __global__ void __launch_bounds__(kThreads, 1)
 k_svr_fact(const DevFact *__restrict__ fc, const DevFTask *__restrict__ tasks, int task0, const double *__restrict__ x, int64_t g_base,
            const uint8_t *__restrict__ valid, const double *__restrict__ blob, const double *__restrict__ w_lrc,
-           const double *__restrict__ exp2_tab, int n_sv_pad, double gamma, double rho, double zero_score, double *__restrict__ out)
+           const double *__restrict__ exp2_tab, int n_sv_pad, double gamma, double rho, double zero_score, double *__restrict__ out,
+           unsigned long long *__restrict__ work)
 {
     extern __shared__ __align__(128) uint8_t smem_raw[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, gid = lane >> 2, tig = lane & 3;
@@ -246,6 +247,13 @@ k_svr_fact(const DevFact *__restrict__ fc, const DevFTask *__restrict__ tasks, i
     // work units of the math warps: 16 rows x all C columns (8 accumulator chains and 8 independent exp chains per
     // lane: the epilogue is latency bound); longest-processing-time assignment
     const int uI = RI >> 4, uQ = RQ >> 4, uA = RA >> 4, n_units = uI + uQ + uA;
+    if (threadIdx.x == 32 && work) {
+        // work this task executes (tasks that returned above add nothing): every 8-row fragment meets C columns
+        const unsigned long long chunks = (unsigned long long)(n_sv_pad / C);
+        atomicAdd(&work[0], chunks * (unsigned long long)(((RA + RQ) / 8 * (FACT_K_ARM / 4) + RI / 8 * (FACT_K_INS / 4)) * (FACT_C / 8)));
+        atomicAdd(&work[1], chunks * (unsigned long long)(R * FACT_C));
+        atomicAdd(&work[2], chunks * (unsigned long long)(n_c * FACT_C));
+    }
     if (threadIdx.x == 0) {
         int load[kMathWarps], cnt[kMathWarps];
         for (int w = 0; w < kMathWarps; w++) load[w] = cnt[w] = 0;
@@ -480,24 +488,8 @@ int launch_svr_fact(mg_ctx *ctx, const mg_panel *p, int ftask0, int ftask1, cons
     mg_time_begin(ctx, TM_SVR, n_cand);
     k_svr_fact<<<ftask1 - ftask0, kThreads, ctx->fact_smem, ctx->stream>>>(ctx->d_fact, p->d_ftasks, ftask0, d_x, g_base, d_valid,
                                                                          ctx->d_fact_blob, d_w, ctx->d_exp2tab, ctx->n_sv_pad, ctx->gamma,
-                                                                         ctx->rho, ctx->zero_score, d_out);
+                                                                         ctx->rho, ctx->zero_score, d_out, ctx->d_work);
     mg_time_end(ctx);
     CUDA_TRY(ctx, cudaGetLastError());
-    // executed work, from the task list: rows are padded to 8, every 8-row fragment meets C columns
-    {
-        const HostConfig &h = ctx->cfg;
-        const DevFact &f = ctx->h_fact;
-        const double chunks = ctx->n_sv_pad / FACT_C;
-        double dmma = 0, ex = 0, ga = 0;
-        for (int t = ftask0; t < ftask1; t++) {
-            const DevFTask &tk = p->h_ftasks[t];
-            const int nA = tk.strand ? f.n_lig : f.n_ext, nQ = tk.strand ? f.n_ext : f.n_lig;
-            const int RA = (tk.nsi * nA + 15) & ~15, RQ = ((tk.nsi + h.max_sum - h.min_sum) * nQ + 15) & ~15, RI = (tk.nsi * f.n_sums + 15) & ~15;
-            dmma += chunks * ((RA + RQ) / 8 * (FACT_K_ARM / 4) + RI / 8 * (FACT_K_INS / 4)) * (FACT_C / 8);
-            ex += chunks * (RA + RQ + RI) * FACT_C;
-            ga += chunks * tk.nsi * f.n_pairs * FACT_C;
-        }
-        ctx->tm.svr_dmma += dmma; ctx->tm.svr_exp += ex; ctx->tm.svr_gather += ga;
-    }
     return MG_OK;
 }

@@ -26,8 +26,8 @@ static cudaEvent_t ev_get(mg_ctx *ctx)
         ctx->ev_free.pop_back();
         return e;
     }
-    cudaEvent_t e;
-    cudaEventCreate(&e);
+    cudaEvent_t e = nullptr;
+    if (cudaEventCreate(&e) != cudaSuccess) return nullptr;  // the launch still runs; only its timing is lost
     return e;
 }
 
@@ -38,14 +38,15 @@ int mg_time_begin(mg_ctx *ctx, int which, long units)
     ep.b = ev_get(ctx);
     ep.which = which;
     ep.units = units;
-    cudaEventRecord(ep.a, ctx->stream);
+    ep.ok = ep.a && ep.b && cudaEventRecord(ep.a, ctx->stream) == cudaSuccess;
     ctx->ev_pending.push_back(ep);
     return MG_OK;
 }
 
 int mg_time_end(mg_ctx *ctx)
 {
-    cudaEventRecord(ctx->ev_pending.back().b, ctx->stream);
+    EventPair &ep = ctx->ev_pending.back();
+    if (ep.ok) ep.ok = cudaEventRecord(ep.b, ctx->stream) == cudaSuccess;
     return MG_OK;
 }
 
@@ -53,13 +54,13 @@ static void drain_timings(mg_ctx *ctx)
 {
     for (auto &ep : ctx->ev_pending) {
         float ms = 0.f;
-        if (cudaEventElapsedTime(&ms, ep.a, ep.b) == cudaSuccess) {
+        if (ep.ok && cudaEventElapsedTime(&ms, ep.a, ep.b) == cudaSuccess) {
             if (ep.which == TM_FEAT) { ctx->tm.ms_feat += ms; ctx->tm.launches_feat++; ctx->tm.candidates_feat += ep.units; }
             else if (ep.which == TM_SVR) { ctx->tm.ms_svr += ms; ctx->tm.launches_svr++; ctx->tm.candidates_svr += ep.units; }
             else { ctx->tm.ms_other += ms; ctx->tm.launches_other++; }
         }
-        ctx->ev_free.push_back(ep.a);
-        ctx->ev_free.push_back(ep.b);
+        if (ep.a) ctx->ev_free.push_back(ep.a);
+        if (ep.b) ctx->ev_free.push_back(ep.b);
     }
     ctx->ev_pending.clear();
 }
@@ -248,6 +249,8 @@ extern "C" int mg_create(int device, mg_ctx **out)
     if ((e = cudaMalloc(&ctx->d_exp2tab, sizeof e2tab)) != cudaSuccess) return fail("cudaMalloc", e);
     cudaMemcpy(ctx->d_exp2tab, e2tab, sizeof e2tab, cudaMemcpyHostToDevice);
     if ((e = cudaMalloc(&ctx->d_cfg, sizeof(DevConfig))) != cudaSuccess) return fail("cudaMalloc", e);
+    if ((e = cudaMalloc(&ctx->d_work, 4 * sizeof(unsigned long long))) != cudaSuccess) return fail("cudaMalloc", e);
+    cudaMemset(ctx->d_work, 0, 4 * sizeof(unsigned long long));
     if ((e = cudaMalloc(&ctx->d_fact, sizeof(DevFact))) != cudaSuccess) return fail("cudaMalloc", e);
     uint8_t lk[MG_NLRC], lc[MG_NLRC];
     for (int i = 0; i < MG_NLRC; i++) {
@@ -285,7 +288,7 @@ extern "C" void mg_destroy(mg_ctx *ctx)
     for (auto e : ctx->ev_free) cudaEventDestroy(e);
     if (ctx->sw_a) { cudaEventDestroy(ctx->sw_a); cudaEventDestroy(ctx->sw_b); }
     free_model(ctx);
-    cudaFree(ctx->d_x); cudaFree(ctx->d_fdesc); cudaFree(ctx->d_fdesc_win); cudaFree(ctx->d_logcopy); cudaFree(ctx->d_exp2tab); cudaFree(ctx->d_cfg); cudaFree(ctx->d_fact);
+    cudaFree(ctx->d_x); cudaFree(ctx->d_fdesc); cudaFree(ctx->d_fdesc_win); cudaFree(ctx->d_logcopy); cudaFree(ctx->d_exp2tab); cudaFree(ctx->d_cfg); cudaFree(ctx->d_fact); cudaFree(ctx->d_work);
     cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
@@ -322,6 +325,7 @@ extern "C" int mg_reset_timings(mg_ctx *ctx)
     CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
     drain_timings(ctx);
     memset(&ctx->tm, 0, sizeof ctx->tm);
+    CUDA_TRY(ctx, cudaMemsetAsync(ctx->d_work, 0, 3 * sizeof(unsigned long long), ctx->stream));
     return MG_OK;
 }
 
@@ -329,11 +333,17 @@ extern "C" int mg_get_timings(mg_ctx *ctx, mg_timings *out)
 {
     CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
     drain_timings(ctx);
-    if (out) *out = ctx->tm;
+    if (out) {
+        *out = ctx->tm;
+        // the factored K-svr counts the work of the tasks that really ran on the device
+        unsigned long long w[3] = {0, 0, 0};
+        CUDA_TRY(ctx, cudaMemcpy(w, ctx->d_work, sizeof w, cudaMemcpyDeviceToHost));
+        out->svr_dmma += (double)w[0]; out->svr_exp += (double)w[1]; out->svr_gather += (double)w[2];
+    }
     return MG_OK;
 }
 
-static int host_config_from(const mg_config *c, HostConfig &h, std::string &err)
+int mg_host_config_from(const mg_config *c, HostConfig &h, std::string &err)
 {
     if (!c) return MG_ERR_INVALID;
     if (c->n_pairs <= 0 || c->n_pairs > MG_MAX_PAIRS || c->n_oligo_sizes > MG_MAX_OLIGO || c->n_oligo_sizes < 0 ||
@@ -361,6 +371,12 @@ static int host_config_from(const mg_config *c, HostConfig &h, std::string &err)
         }
         h.max_sum = std::max(h.max_sum, s);
         h.min_sum = std::min(h.min_sum, s);
+        // the tile loop walks arm sums in descending order, each sum's list once (mipgen.cpp:431-438); the replay of its
+        // score-dependent skips (mg_tile_replay, K-condense) relies on pairs grouped by sum, sums strictly descending
+        if (i > 0 && s > h.ext_len[i - 1] + h.lig_len[i - 1]) {
+            err = "mg_config: arm pairs must be grouped by arm sum with sums in descending order (mipgen.cpp:431-438)";
+            return MG_ERR_INVALID;
+        }
     }
     return MG_OK;
 }
@@ -369,7 +385,7 @@ extern "C" int mg_set_config(mg_ctx *ctx, const mg_config *c)
 {
     if (!ctx || !c) return MG_ERR_INVALID;
     HostConfig h;
-    int hrc = host_config_from(c, h, ctx->err);
+    int hrc = mg_host_config_from(c, h, ctx->err);
     if (hrc != MG_OK) return hrc;
     DevConfig *d = new DevConfig();
     memset(d, 0, sizeof *d);
@@ -393,6 +409,7 @@ extern "C" int mg_set_config(mg_ctx *ctx, const mg_config *c)
     if (e != cudaSuccess) { ctx->err = std::string("config upload: ") + cudaGetErrorString(e); return MG_ERR_CUDA; }
     ctx->cfg = h;
     ctx->has_cfg = true;
+    ctx->cfg_serial++;
 
     // factored SVR: distinct arm lengths / arm sums, and the largest window whose tables fit in shared memory
     ctx->fact_ok = false;
@@ -647,15 +664,16 @@ static int predict_rows(mg_ctx *ctx, const double *x, long n, long ld, double *o
         long m = std::min<long>(kMaxChunkRows, n - i0);
         int rc = ensure_x(ctx, m);
         if (rc != MG_OK) return rc;
-        if (!d_out) CUDA_TRY(ctx, cudaMalloc(&d_out, (size_t)std::min<long>(n, kMaxChunkRows) * 8));
+        if (!d_out) CUDA_TRY(ctx, mg_dev_alloc(ctx, (void **)&d_out, (size_t)std::min<long>(n, kMaxChunkRows) * 8));
         CUDA_TRY(ctx, cudaMemcpy2DAsync(ctx->d_x, MG_NFEAT * 8, x + i0 * ld, (size_t)ld * 8, MG_NFEAT * 8, (size_t)m,
                                          cudaMemcpyHostToDevice, ctx->stream));
         rc = direct ? launch_svr_direct(ctx, ctx->d_x, m, MG_NFEAT, d_out) : launch_svr(ctx, ctx->d_x, m, nullptr, d_out);
-        if (rc != MG_OK) { cudaFree(d_out); return rc; }
-        CUDA_TRY(ctx, cudaMemcpyAsync(out + i0, d_out, (size_t)m * 8, cudaMemcpyDeviceToHost, ctx->stream));
-        CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+        if (rc != MG_OK) { mg_dev_free(ctx, d_out); return rc; }
+        cudaError_t e = cudaMemcpyAsync(out + i0, d_out, (size_t)m * 8, cudaMemcpyDeviceToHost, ctx->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+        if (e != cudaSuccess) { ctx->err = std::string("mg_svr_predict: ") + cudaGetErrorString(e); mg_dev_free(ctx, d_out); return MG_ERR_CUDA; }
     }
-    cudaFree(d_out);
+    mg_dev_free(ctx, d_out);
     return MG_OK;
 }
 
@@ -757,7 +775,7 @@ extern "C" int mg_score_candidates(mg_ctx *ctx, const mg_candidate *cands, long 
 // ---------------------------------------------------------------------------
 // region grids
 // ---------------------------------------------------------------------------
-static int first_scan_start(const HostConfig &c, const mg_region *r)
+int mg_host_first_scan(const HostConfig &c, const mg_region *r)
 {
     if (r->scan_begin > 0) return r->scan_begin;
     // mipgen.cpp:421-425 (the loop pre-increments)
@@ -766,35 +784,35 @@ static int first_scan_start(const HostConfig &c, const mg_region *r)
     return cur + 1;
 }
 
-static int n_scan(const HostConfig &c, const mg_region *r)
+int mg_host_n_scan(const HostConfig &c, const mg_region *r)
 {
     int last = (r->scan_begin > 0 && r->scan_end > 0) ? r->scan_end : r->stop_flanked;
-    int n = last - first_scan_start(c, r) + 1;
+    int n = last - mg_host_first_scan(c, r) + 1;
     return n < 0 ? 0 : n;
 }
 
-extern "C" int mg_first_scan_start(const mg_ctx *ctx, const mg_region *r) { return (ctx && ctx->has_cfg && r) ? first_scan_start(ctx->cfg, r) : 0; }
+extern "C" int mg_first_scan_start(const mg_ctx *ctx, const mg_region *r) { return (ctx && ctx->has_cfg && r) ? mg_host_first_scan(ctx->cfg, r) : 0; }
 
 extern "C" int64_t mg_grid_size(const mg_ctx *ctx, const mg_region *r)
 {
     if (!ctx || !ctx->has_cfg || !r) return 0;
-    return (int64_t)n_scan(ctx->cfg, r) * ctx->cfg.n_cap * (int64_t)ctx->cfg.ext_len.size() * 2;
+    return (int64_t)mg_host_n_scan(ctx->cfg, r) * ctx->cfg.n_cap * (int64_t)ctx->cfg.ext_len.size() * 2;
 }
 
 extern "C" int64_t mg_config_grid_size(const mg_config *cfg, const mg_region *r)
 {
     HostConfig h;
     std::string err;
-    if (!r || host_config_from(cfg, h, err) != MG_OK) return -1;
-    return (int64_t)n_scan(h, r) * h.n_cap * (int64_t)h.ext_len.size() * 2;
+    if (!r || mg_host_config_from(cfg, h, err) != MG_OK) return -1;
+    return (int64_t)mg_host_n_scan(h, r) * h.n_cap * (int64_t)h.ext_len.size() * 2;
 }
 
 extern "C" int mg_config_first_scan_start(const mg_config *cfg, const mg_region *r)
 {
     HostConfig h;
     std::string err;
-    if (!r || host_config_from(cfg, h, err) != MG_OK) return -1;
-    return first_scan_start(h, r);
+    if (!r || mg_host_config_from(cfg, h, err) != MG_OK) return -1;
+    return mg_host_first_scan(h, r);
 }
 
 extern "C" void mg_panel_destroy(mg_panel *p)
@@ -804,6 +822,7 @@ extern "C" void mg_panel_destroy(mg_panel *p)
     mg_ctx *c = p->ctx;
     mg_dev_free(c, p->d_ftasks); mg_dev_free(c, p->d_w);
     mg_dev_free(c, p->d_regions); mg_dev_free(c, p->d_tasks); mg_dev_free(c, p->d_codes); mg_dev_free(c, p->d_lrc); mg_dev_free(c, p->d_copies);
+    mg_dev_free(c, p->d_maskpf); mg_dev_free(c, p->d_snppf); mg_dev_free(c, p->d_unmap);
     mg_dev_free(c, p->d_valid); mg_dev_free(c, p->d_logistic); mg_dev_free(c, p->d_svr); mg_dev_free(c, p->d_feat);
     delete p;
 }
@@ -816,11 +835,12 @@ extern "C" int mg_panel_create(mg_ctx *ctx, const mg_region *regions, int n, mg_
     CUDA_TRY(ctx, cudaSetDevice(ctx->device));
     mg_panel *p = new mg_panel();
     p->ctx = ctx;
+    p->cfg_serial = ctx->cfg_serial;
     p->n_regions = n;
     p->offsets.assign(n + 1, 0);
     p->h_regions.resize(std::max(n, 1));
-    int64_t codes = 0, copies = 0;
-    bool any_lrc = false;
+    int64_t codes = 0, copies = 0, unmap = 0;
+    bool any_lrc = false, any_snp = false;
     const int n_oligo = (int)ctx->cfg.oligo_sizes.size();
     for (int i = 0; i < n; i++) {
         const mg_region &r = regions[i];
@@ -839,10 +859,16 @@ extern "C" int mg_panel_create(mg_ctx *ctx, const mg_region *regions, int n, mg_
         d.copy_off = r.copies ? copies : -1;
         d.seq_len = r.seq_len; d.seq_start = r.seq_start; d.seq_stop = r.seq_stop;
         d.start_flanked = r.start_flanked; d.stop_flanked = r.stop_flanked;
-        d.first_scan = first_scan_start(ctx->cfg, &r); d.n_scan = n_scan(ctx->cfg, &r); d.pad = 0;
+        d.first_scan = mg_host_first_scan(ctx->cfg, &r); d.n_scan = mg_host_n_scan(ctx->cfg, &r);
+        d.has_snp = r.snp != nullptr;
+        d.aux_off = codes + i;  // seq_len + 1 prefix entries per region
+        d.unmap_off = r.unmappable ? unmap : -1;
         codes += r.seq_len;
         if (r.copies) copies += (int64_t)n_oligo * r.seq_len;
+        if (r.unmappable) unmap += (int64_t)ctx->cfg.n_cap * r.seq_len;
         any_lrc |= r.lrc != nullptr;
+        any_snp |= r.snp != nullptr;
+        p->has_sel_inputs |= r.masked_seq || r.snp || r.unmappable;
         p->offsets[i + 1] = p->offsets[i] + mg_grid_size(ctx, &r);
     }
     p->n_cand = p->offsets[n];
@@ -902,11 +928,23 @@ extern "C" int mg_panel_create(mg_ctx *ctx, const mg_region *regions, int n, mg_
         std::vector<char> ascii((size_t)codes);
         std::vector<double> lrc(any_lrc ? (size_t)n * MG_NLRC : 0, 0.0);
         std::vector<int> cp((size_t)copies);
+        // selection-only inputs: prefix counts of masked ('N') bases and of SNP positions per region, unmappable MIP starts
+        std::vector<int> maskpf((size_t)(codes + n)), snppf(any_snp ? (size_t)(codes + n) : 0, 0);
+        std::vector<uint8_t> um((size_t)unmap);
         for (int i = 0; i < n; i++) {
             const mg_region &r = regions[i];
             memcpy(&ascii[p->h_regions[i].seq_off], r.seq, r.seq_len);
             if (r.lrc) memcpy(&lrc[(size_t)i * MG_NLRC], r.lrc, MG_NLRC * 8);
             if (r.copies) memcpy(&cp[p->h_regions[i].copy_off], r.copies, (size_t)n_oligo * r.seq_len * sizeof(int));
+            const char *ms = r.masked_seq ? r.masked_seq : r.seq;  // -trf off: the masked copy IS the sequence (mipgen.cpp:1058-1062)
+            int *mp = &maskpf[(size_t)p->h_regions[i].aux_off];
+            mp[0] = 0;
+            for (int k = 0; k < r.seq_len; k++) mp[k + 1] = mp[k] + (ms[k] == 'N');
+            if (r.snp) {
+                int *sp = &snppf[(size_t)p->h_regions[i].aux_off];
+                for (int k = 0; k < r.seq_len; k++) sp[k + 1] = sp[k] + (r.snp[k] != 0);
+            }
+            if (r.unmappable) memcpy(&um[(size_t)p->h_regions[i].unmap_off], r.unmappable, (size_t)ctx->cfg.n_cap * r.seq_len);
         }
         char *d_ascii = nullptr;
         P_TRY(mg_dev_alloc(ctx, (void **)&d_ascii, (size_t)codes));
@@ -930,6 +968,16 @@ extern "C" int mg_panel_create(mg_ctx *ctx, const mg_region *regions, int n, mg_
             P_TRY(mg_dev_alloc(ctx, (void **)&p->d_copies, (size_t)copies * sizeof(int)));
             P_TRY(cudaMemcpyAsync(p->d_copies, cp.data(), (size_t)copies * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
         }
+        P_TRY(mg_dev_alloc(ctx, (void **)&p->d_maskpf, maskpf.size() * sizeof(int)));
+        P_TRY(cudaMemcpyAsync(p->d_maskpf, maskpf.data(), maskpf.size() * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+        if (any_snp) {
+            P_TRY(mg_dev_alloc(ctx, (void **)&p->d_snppf, snppf.size() * sizeof(int)));
+            P_TRY(cudaMemcpyAsync(p->d_snppf, snppf.data(), snppf.size() * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+        }
+        if (unmap > 0) {
+            P_TRY(mg_dev_alloc(ctx, (void **)&p->d_unmap, (size_t)unmap));
+            P_TRY(cudaMemcpyAsync(p->d_unmap, um.data(), (size_t)unmap, cudaMemcpyHostToDevice, ctx->stream));
+        }
         int rc = launch_encode(ctx, d_ascii, p->d_codes, codes);
         cudaStreamSynchronize(ctx->stream);  // host staging vectors go out of scope
         mg_dev_free(ctx, d_ascii);
@@ -943,9 +991,13 @@ extern "C" int mg_panel_create(mg_ctx *ctx, const mg_region *regions, int n, mg_
 
 extern "C" int64_t mg_panel_candidates(const mg_panel *p) { return p ? p->n_cand : 0; }
 
+// a panel caches grid offsets, windows and task lists derived from the config it was created under
+static const char *const kStalePanel = "the panel was created under an earlier mg_set_config: create it again";
+
 extern "C" int mg_panel_score(mg_ctx *ctx, mg_panel *p, int want)
 {
     if (!ctx || !p || p->ctx != ctx) return MG_ERR_INVALID;
+    if (p->cfg_serial != ctx->cfg_serial) { ctx->err = kStalePanel; return MG_ERR_INVALID; }
     if ((want & MG_WANT_SVR) && !ctx->has_model) { ctx->err = "no SVR model loaded"; return MG_ERR_NOMODEL; }
     if (p->n_cand == 0) return MG_OK;
     CUDA_TRY(ctx, cudaSetDevice(ctx->device));
@@ -1013,6 +1065,7 @@ extern "C" int mg_panel_score(mg_ctx *ctx, mg_panel *p, int want)
 extern "C" int mg_panel_fetch(mg_ctx *ctx, mg_panel *p, uint8_t *valid, double *logistic, double *svr, double *features)
 {
     if (!ctx || !p || p->ctx != ctx) return MG_ERR_INVALID;
+    if (p->cfg_serial != ctx->cfg_serial) { ctx->err = kStalePanel; return MG_ERR_INVALID; }
     CUDA_TRY(ctx, cudaSetDevice(ctx->device));
     if (p->n_cand > 0) {
         if ((valid && !p->has_valid) || (logistic && !p->has_logistic) || (svr && !p->has_svr) || (features && !p->has_feat)) {
@@ -1040,13 +1093,14 @@ extern "C" int mg_panel_device_ptrs(const mg_panel *p, const uint8_t **valid, co
 extern "C" int64_t mg_panel_valid_candidates(const mg_panel *p)
 {
     if (!p || !p->has_valid || p->n_cand == 0) return 0;
-    std::vector<uint8_t> v((size_t)p->n_cand);
-    cudaSetDevice(p->ctx->device);
-    cudaStreamSynchronize(p->ctx->stream);
-    if (cudaMemcpy(v.data(), p->d_valid, v.size(), cudaMemcpyDeviceToHost) != cudaSuccess) return -1;
-    int64_t c = 0;
-    for (uint8_t b : v) c += b;
-    return c;
+    mg_ctx *ctx = p->ctx;
+    if (cudaSetDevice(ctx->device) != cudaSuccess) return -1;
+    unsigned long long *d_count = ctx->d_work + 3, h = 0;  // the context's scratch counter word
+    if (cudaMemsetAsync(d_count, 0, sizeof h, ctx->stream) != cudaSuccess) return -1;
+    if (launch_count_valid(ctx, p->d_valid, p->n_cand, d_count) != MG_OK) return -1;
+    if (cudaMemcpyAsync(&h, d_count, sizeof h, cudaMemcpyDeviceToHost, ctx->stream) != cudaSuccess) return -1;
+    if (cudaStreamSynchronize(ctx->stream) != cudaSuccess) return -1;
+    return (int64_t)h;
 }
 
 extern "C" int mg_score_regions(mg_ctx *ctx, const mg_region *regions, int n, int want, int64_t *out_offsets, uint8_t *valid,
@@ -1071,19 +1125,20 @@ extern "C" int mg_score_regions(mg_ctx *ctx, const mg_region *regions, int n, in
 // ---------------------------------------------------------------------------
 // selection front-end
 // ---------------------------------------------------------------------------
-extern "C" int mg_region_scan_count(const mg_ctx *ctx, const mg_region *r) { return (ctx && ctx->has_cfg && r) ? n_scan(ctx->cfg, r) : 0; }
+extern "C" int mg_region_scan_count(const mg_ctx *ctx, const mg_region *r) { return (ctx && ctx->has_cfg && r) ? mg_host_n_scan(ctx->cfg, r) : 0; }
 
-static int n_positions(const HostConfig &c, const mg_region *r)
+int mg_host_n_positions(const HostConfig &c, const mg_region *r)
 {
-    int n = r->stop_flanked + c.max_capture - c.min_sum - 1 - first_scan_start(c, r) + 1;
+    int n = r->stop_flanked + c.max_capture - c.min_sum - 1 - mg_host_first_scan(c, r) + 1;
     return n < 0 ? 0 : n;
 }
 
-extern "C" int mg_region_position_count(const mg_ctx *ctx, const mg_region *r) { return (ctx && ctx->has_cfg && r) ? n_positions(ctx->cfg, r) : 0; }
+extern "C" int mg_region_position_count(const mg_ctx *ctx, const mg_region *r) { return (ctx && ctx->has_cfg && r) ? mg_host_n_positions(ctx->cfg, r) : 0; }
 
 extern "C" int mg_panel_select(mg_ctx *ctx, mg_panel *p, const mg_select_params *sp, int64_t *scan_best, int64_t *pos_best)
 {
     if (!ctx || !p || p->ctx != ctx || !sp || !scan_best || !pos_best) return MG_ERR_INVALID;
+    if (p->cfg_serial != ctx->cfg_serial) { ctx->err = kStalePanel; return MG_ERR_INVALID; }
     const double *d_score = sp->method == 1 ? (p->has_svr ? p->d_svr : nullptr) : (p->has_logistic ? p->d_logistic : nullptr);
     if (!d_score) { ctx->err = "mg_panel_select: the panel has not been scored with the scores this method selects on"; return MG_ERR_INVALID; }
     CUDA_TRY(ctx, cudaSetDevice(ctx->device));
@@ -1103,8 +1158,7 @@ extern "C" int mg_panel_select(mg_ctx *ctx, mg_panel *p, const mg_select_params 
     S_TRY(mg_dev_alloc(ctx, (void **)&d_pb, (size_t)std::max<int64_t>(po[n], 1) * 16));
     S_TRY(cudaMemcpyAsync(d_so, so.data(), (size_t)(n + 1) * 8, cudaMemcpyHostToDevice, ctx->stream));
     S_TRY(cudaMemcpyAsync(d_po, po.data(), (size_t)(n + 1) * 8, cudaMemcpyHostToDevice, ctx->stream));
-    int rc = launch_select(ctx, p, d_so, d_po, so[n], po[n], d_score, sp->method, sp->heuristic, sp->lower_score_limit,
-                           sp->upper_score_limit, sp->max_arm_copy, sp->target_arm_copy, d_sb, d_pb);
+    int rc = launch_select(ctx, p, d_so, d_po, so[n], po[n], d_score, sp, d_sb, d_pb);
     if (rc == MG_OK) {
         S_TRY(cudaMemcpyAsync(scan_best, d_sb, (size_t)so[n] * 16, cudaMemcpyDeviceToHost, ctx->stream));
         S_TRY(cudaMemcpyAsync(pos_best, d_pb, (size_t)po[n] * 16, cudaMemcpyDeviceToHost, ctx->stream));
@@ -1117,6 +1171,33 @@ extern "C" int mg_panel_select(mg_ctx *ctx, mg_panel *p, const mg_select_params 
     return rc;
 }
 
+extern "C" int mg_panel_gather(mg_ctx *ctx, mg_panel *p, const int64_t *idx, int64_t n, double *logistic, double *svr)
+{
+    if (!ctx || !p || p->ctx != ctx || n < 0 || (n > 0 && !idx)) return MG_ERR_INVALID;
+    if ((logistic && !p->has_logistic) || (svr && !p->has_svr)) { ctx->err = "mg_panel_gather: requested score was never computed"; return MG_ERR_INVALID; }
+    if (n == 0 || (!logistic && !svr)) return MG_OK;
+    for (int64_t i = 0; i < n; i++)
+        if (idx[i] >= p->n_cand) { ctx->err = "mg_panel_gather: grid index outside the panel"; return MG_ERR_INVALID; }
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    int64_t *d_idx = nullptr;
+    double *d_a = nullptr, *d_b = nullptr;
+    auto cleanup = [&]() { mg_dev_free(ctx, d_idx); mg_dev_free(ctx, d_a); mg_dev_free(ctx, d_b); };
+#define G_TRY(expr) do { cudaError_t _e = (expr); if (_e != cudaSuccess) { ctx->err = std::string(#expr) + ": " + cudaGetErrorString(_e); cudaStreamSynchronize(ctx->stream); cleanup(); return MG_ERR_CUDA; } } while (0)
+    G_TRY(mg_dev_alloc(ctx, (void **)&d_idx, (size_t)n * 8));
+    if (logistic) G_TRY(mg_dev_alloc(ctx, (void **)&d_a, (size_t)n * 8));
+    if (svr) G_TRY(mg_dev_alloc(ctx, (void **)&d_b, (size_t)n * 8));
+    G_TRY(cudaMemcpyAsync(d_idx, idx, (size_t)n * 8, cudaMemcpyHostToDevice, ctx->stream));
+    int rc = launch_gather(ctx, d_idx, n, p->d_logistic, d_a, p->d_svr, d_b);
+    if (rc == MG_OK) {
+        if (logistic) G_TRY(cudaMemcpyAsync(logistic, d_a, (size_t)n * 8, cudaMemcpyDeviceToHost, ctx->stream));
+        if (svr) G_TRY(cudaMemcpyAsync(svr, d_b, (size_t)n * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    }
+    G_TRY(cudaStreamSynchronize(ctx->stream));
+#undef G_TRY
+    cleanup();
+    return rc;
+}
+
 // ---------------------------------------------------------------------------
 // host helper: the score-dependent control flow of the tile loop
 // ---------------------------------------------------------------------------
@@ -1125,8 +1206,8 @@ extern "C" int64_t mg_tile_replay(const mg_config *cfg, const mg_region *r, cons
 {
     HostConfig c;
     std::string err;
-    if (!r || !valid || !score || host_config_from(cfg, c, err) != MG_OK) return -1;
-    const int n_pairs = (int)c.ext_len.size(), ns = n_scan(c, r);
+    if (!r || !valid || !score || mg_host_config_from(cfg, c, err) != MG_OK) return -1;
+    const int n_pairs = (int)c.ext_len.size(), ns = mg_host_n_scan(c, r);
     // arm-sum groups: maximal runs of pairs with equal ext+lig (mipgen.cpp:431, 438)
     std::vector<std::pair<int, int>> groups;
     for (int p = 0; p < n_pairs;) {
@@ -1171,8 +1252,8 @@ extern "C" int mg_describe_candidates(const mg_config *cfg, const mg_region *r, 
 {
     HostConfig c;
     std::string err;
-    if (!r || (n > 0 && (!idx || !out)) || host_config_from(cfg, c, err) != MG_OK) return MG_ERR_INVALID;
-    const int n_pairs = (int)c.ext_len.size(), ns = n_scan(c, r), s0 = first_scan_start(c, r);
+    if (!r || (n > 0 && (!idx || !out)) || mg_host_config_from(cfg, c, err) != MG_OK) return MG_ERR_INVALID;
+    const int n_pairs = (int)c.ext_len.size(), ns = mg_host_n_scan(c, r), s0 = mg_host_first_scan(c, r);
     const int64_t grid = (int64_t)ns * c.n_cap * n_pairs * 2;
     auto copy_of = [&](int start, int len) {  // mipgen.cpp:612-613; an absent key reads as 0
         if (!r->copies) return 1;
@@ -1211,6 +1292,9 @@ extern "C" int64_t mg_format_mip_record(const mg_region *r, const mg_mip_info *m
                                         char *buf, int64_t cap)
 {
     if (!r || !r->seq || !m || !chr || !label || !universal_middle || !buf || cap <= 0) return -1;
+    // the failure flags are printed as "000": a region that declares TRF / SNP / mappability inputs may need other flags
+    // (and _SNP_ name suffixes, mipgen.cpp:790-792) that only design_mip can derive -- refuse rather than print a wrong record
+    if (r->masked_seq || r->snp || r->unmappable) return -1;
     // the three strings as the object holds them: genomic on '+', reverse-complemented on '-'
     auto cut = [&](int start, int stop, std::string &out) {
         const int a = start - r->seq_start, n = stop - start + 1;
@@ -1225,11 +1309,14 @@ extern "C" int64_t mg_format_mip_record(const mg_region *r, const mg_mip_info *m
     std::string ext, lig, tgt;
     if (!cut(m->ext_start, m->ext_stop, ext) || !cut(m->lig_start, m->lig_stop, lig) || !cut(m->scan_start, m->scan_stop, tgt)) return -1;
     const char strand = m->strand ? '-' : '+';
-    char head[256], mid[192], tail[160];
-    snprintf(head, sizeof head, "%s:%d-%d/%d,%d/%c\t%g\t%s\t%d\t%d\t%d\t", chr, m->strand ? m->lig_start : m->ext_start,
-             m->strand ? m->ext_stop : m->lig_stop, m->ext_len, m->lig_len, strand, score, chr, m->ext_start, m->ext_stop, m->ext_copy);
+    char head[160], mid[192], tail[160];  // numbers only: the chromosome name, of any length, goes in as a string
+    std::string rec = chr;
+    snprintf(head, sizeof head, ":%d-%d/%d,%d/%c\t%g\t", m->strand ? m->lig_start : m->ext_start, m->strand ? m->ext_stop : m->lig_stop,
+             m->ext_len, m->lig_len, strand, score);
+    rec += head; rec += chr;
+    snprintf(head, sizeof head, "\t%d\t%d\t%d\t", m->ext_start, m->ext_stop, m->ext_copy);
+    rec += head;
     snprintf(mid, sizeof mid, "\t%d\t%d\t%d\t", m->lig_start, m->lig_stop, m->lig_copy);
-    std::string rec = head;
     rec += ext; rec += mid; rec += lig;
     snprintf(mid, sizeof mid, "\t%d\t%d\t", m->scan_start, m->scan_stop);
     rec += mid; rec += tgt; rec += '\t';

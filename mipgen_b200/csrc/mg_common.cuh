@@ -37,7 +37,9 @@ struct DevRegion {
     int seq_len, seq_start, seq_stop;
     int start_flanked, stop_flanked;
     int first_scan, n_scan;
-    int pad;
+    int has_snp;        // the panel's snp prefix array has entries for this region
+    int64_t aux_off;    // first entry of this region in the panel's masked / snp prefix arrays (seq_len + 1 entries each)
+    int64_t unmap_off;  // offset of this region's [n_cap][seq_len] unmappable-start bytes, or -1
 };
 
 // one K-feat work item: a window of consecutive scan starts of one region, restricted to a range of
@@ -148,7 +150,7 @@ struct HostConfig {
     int n_cap = 0, max_sum = 0, min_sum = 0, max_arm = 0, min_arm = 0;
 };
 
-struct EventPair { cudaEvent_t a, b; int which; long units; };
+struct EventPair { cudaEvent_t a, b; int which; long units; bool ok; };
 struct CachedBlock { void *ptr; size_t bytes; };
 
 struct mg_ctx {
@@ -157,6 +159,7 @@ struct mg_ctx {
     std::string err;
     // config
     bool has_cfg = false;
+    long cfg_serial = 0;  // bumped by every mg_set_config: panels remember the one they were built under
     HostConfig cfg;
     DevConfig *d_cfg = nullptr;
     // tables
@@ -164,6 +167,8 @@ struct mg_ctx {
     uint32_t *d_fdesc_win = nullptr;  // [192] the same with prefix-table rows (window front-end)
     double *d_logcopy = nullptr;    // [102] log10(copy) for copy 0..100 (glibc), [101] = 2.0
     double *d_exp2tab = nullptr;    // [64] 2^(j/64), K-svr's exp table
+    unsigned long long *d_work = nullptr;  // [0..2] DMMAs, exp elements, gathered triples EXECUTED by the factored K-svr since the
+                                           // last mg_reset_timings (tasks that exit after the claim phase add nothing); [3] scratch
     // model
     bool has_model = false;
     int n_sv = 0, n_sv_pad = 0;
@@ -199,6 +204,7 @@ struct mg_ctx {
 
 struct mg_panel {
     mg_ctx *ctx = nullptr;
+    long cfg_serial = 0;
     int n_regions = 0;
     int64_t n_cand = 0;
     int64_t n_valid_static = 0;
@@ -219,6 +225,10 @@ struct mg_panel {
     int64_t n_codes = 0;
     double *d_lrc = nullptr;       // [n_regions][44]
     int *d_copies = nullptr;
+    int *d_maskpf = nullptr;       // per region: prefix counts of 'N' in the masked sequence (seq_len + 1 entries)
+    int *d_snppf = nullptr;        // per region: prefix counts of SNP positions, or null
+    uint8_t *d_unmap = nullptr;    // [n_cap][seq_len] per region that declares unmappable MIP starts, or null
+    bool has_sel_inputs = false;   // some region carries masked_seq / snp / unmappable
     uint8_t *d_valid = nullptr;
     double *d_logistic = nullptr;
     double *d_svr = nullptr;
@@ -234,6 +244,12 @@ struct mg_panel {
             return MG_ERR_CUDA;                                                              \
         }                                                                                    \
     } while (0)
+
+// host arithmetic shared by mg_api.cu and mg_tile.cu
+int mg_host_config_from(const mg_config *c, HostConfig &h, std::string &err);
+int mg_host_first_scan(const HostConfig &c, const mg_region *r);      // mipgen.cpp:421-425
+int mg_host_n_scan(const HostConfig &c, const mg_region *r);
+int mg_host_n_positions(const HostConfig &c, const mg_region *r);     // first scan start .. stop_flanked + max_capture - min_sum - 1
 
 // caching device allocator (mg_api.cu): stream-ordered reuse on the context's single stream
 cudaError_t mg_dev_alloc(mg_ctx *ctx, void **out, size_t bytes);
@@ -261,8 +277,9 @@ int launch_svr(mg_ctx *ctx, const double *d_x, int64_t n, const uint8_t *d_valid
 int launch_svr_setup(mg_ctx *ctx);
 int launch_fact_setup(mg_ctx *ctx);
 int launch_select(mg_ctx *ctx, const mg_panel *p, const int64_t *d_scan_off, const int64_t *d_pos_off, int64_t total_scan,
-                  int64_t total_pos, const double *d_score, int method, int heuristic, double lower, double upper, int max_arm_copy,
-                  int target_arm_copy, int64_t *d_scan_best, int64_t *d_pos_best);
+                  int64_t total_pos, const double *d_score, const mg_select_params *sp, int64_t *d_scan_best, int64_t *d_pos_best);
+int launch_gather(mg_ctx *ctx, const int64_t *d_idx, int64_t n, const double *d_a, double *d_out_a, const double *d_b, double *d_out_b);
+int launch_count_valid(mg_ctx *ctx, const uint8_t *d_valid, int64_t n, unsigned long long *d_count);
 int launch_lrc_weights(mg_ctx *ctx, const mg_panel *p, double *d_w);
 int launch_svr_fact(mg_ctx *ctx, const mg_panel *p, int ftask0, int ftask1, const double *d_x, int64_t g_base, int64_t n_cand,
                     const uint8_t *d_valid, const double *d_w, double *d_out);

@@ -79,6 +79,10 @@ class Region:
     flank_seq: Optional[bytes] = None      # region +- (max_capture+1000): input of the lrc
     label: str = "r"
     copies: Optional[np.ndarray] = None    # int32[n_oligo_sizes, len(seq)] or None (=> all 1)
+    # selection-only inputs (mipgen.cpp:606-625, 634-760); None = absent
+    masked_seq: Optional[bytes] = None     # masked_chromosomal_sequence: len(seq) characters, 'N' = TRF-masked
+    snp: Optional[np.ndarray] = None       # uint8[len(seq)]: 1 where chr_snp_positions has an entry
+    unmappable: Optional[np.ndarray] = None  # uint8[n_captures, len(seq)]: 1 where a MIP of that capture size starting here maps ambiguously
 
 
 @dataclass

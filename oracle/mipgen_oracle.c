@@ -661,10 +661,45 @@ int orc_n_positions(const orc_region *r, const orc_cfg *c)
     return n < 0 ? 0 : n;
 }
 
+/* what design_mip leaves in the object for the selection code (mipgen.cpp:606-625, 634-760) */
+typedef struct { double masked; int snp, mapping_failed; } orc_selmip;
+
+static int count_in(const char *s, int seq_len, int off, int len, char what)
+{
+    /* std::string::substr(off, len) clamps the length; std::count over the piece */
+    int n = 0;
+    if (off < 0 || off > seq_len) return 0;
+    for (int i = off; i < off + len && i < seq_len; i++) n += s[i] == what;
+    return n;
+}
+
+static void sel_fields(const orc_region *r, const orc_cfg *c, const orc_sel *sel, const orc_dec *d, orc_selmip *m)
+{
+    orc_geom g;
+    orc_geometry(d->s, d->scan_stop, d->e, d->l, d->strand, &g);
+    const char *masked = sel->masked_seq ? sel->masked_seq : r->seq;
+    double ext_n = count_in(masked, r->seq_len, g.ext_start - r->seq_start, d->e, 'N');   /* :606-609 */
+    double lig_n = count_in(masked, r->seq_len, g.lig_start - r->seq_start, d->l, 'N');
+    m->masked = (ext_n + lig_n) / (d->l + d->e);                                          /* :610 */
+    m->mapping_failed = 0;
+    m->snp = 0;
+    if (sel->unmappable) {                                                                /* :615-625 */
+        int mip_start = (d->strand ? g.lig_start : g.ext_start) - r->seq_start;           /* get_mip_start() */
+        if (mip_start >= 0 && mip_start < r->seq_len && sel->unmappable[(long)d->ci * r->seq_len + mip_start]) {
+            m->mapping_failed = 1;
+            return;  /* design_mip returns before the SNP scan */
+        }
+    }
+    if (sel->snp) {                                                                       /* :634-636, 698-700 */
+        for (int i = g.ext_start; i <= g.ext_stop; i++) { int o = i - r->seq_start; if (o >= 0 && o < r->seq_len && sel->snp[o]) m->snp++; }
+        for (int i = g.lig_start; i <= g.lig_stop; i++) { int o = i - r->seq_start; if (o >= 0 && o < r->seq_len && sel->snp[o]) m->snp++; }
+    }
+}
+
 void orc_condense(const orc_region *r, const orc_cfg *c, const orc_sel *sel, const double *score,
                   const long *enum_idx, long n_enum, long *scan_best)
 {
-    /* mipgen.cpp:1670-1746 with arm_fraction_masked = 0, snp_count = 0, mapping_failed = '0' */
+    /* mipgen.cpp:1670-1746 */
     int nscan = orc_n_scan(r, c);
     for (long i = 0; i < 2L * nscan; i++) scan_best[i] = -1;
     /* the candidates of one scan start are contiguous in enum_idx; walk each block backwards per strand */
@@ -673,26 +708,39 @@ void orc_condense(const orc_region *r, const orc_cfg *c, const orc_sel *sel, con
         orc_dec d0; decode_idx(r, c, enum_idx[b], &d0);
         long e = b;
         while (e < n_enum) { orc_dec d; decode_idx(r, c, enum_idx[e], &d); if (d.si != d0.si) break; e++; }
-        int chosen_copy_count = 0;
+        int chosen_copy_count = 0;                  /* :1677-1680: declared per position, outside the strand loop */
+        double chosen_masked_arm_proportion = 0.0;
         for (int strand = 0; strand < 2; strand++) {
             int skip_ahead = 0;
             long best = -1;
+            int best_snp = 0;
             for (long k = e - 1; k >= b; k--) {
                 if (skip_ahead) continue;
                 orc_dec d; decode_idx(r, c, enum_idx[k], &d);
                 if (d.strand != strand) continue;
                 if (d.ext_copy * d.lig_copy > sel->max_arm_copy) continue;                 /* :1689 */
+                orc_selmip m; sel_fields(r, c, sel, &d, &m);
+                if (m.mapping_failed) continue;                                            /* :1690 */
                 int current = d.ext_copy > d.lig_copy ? d.ext_copy : d.lig_copy;          /* :1692 */
+                double current_masked = m.masked;                                         /* :1693 */
                 double sc = score[enum_idx[k]];
-                if (best < 0) { best = enum_idx[k]; chosen_copy_count = current; }         /* :1695-1700 */
-                else if (current > sel->target_arm_copy && current < chosen_copy_count) {  /* :1709 */
-                    best = enum_idx[k]; chosen_copy_count = current;
+                if (best < 0) {                                                            /* :1695-1700 */
+                    best = enum_idx[k]; best_snp = m.snp; chosen_masked_arm_proportion = current_masked; chosen_copy_count = current;
+                } else if (current_masked > sel->masked_arm_threshold && current_masked < chosen_masked_arm_proportion) {  /* :1701-1706 */
+                    best = enum_idx[k]; best_snp = m.snp; chosen_masked_arm_proportion = current_masked; chosen_copy_count = current;
+                } else if (current > sel->target_arm_copy && current < chosen_copy_count) {  /* :1709-1714 */
+                    best = enum_idx[k]; best_snp = m.snp; chosen_masked_arm_proportion = current_masked; chosen_copy_count = current;
                 } else if (current <= sel->target_arm_copy) {                              /* :1715 */
-                    if (sc < sel->lower_score_limit && sc > score[best]) { best = enum_idx[k]; chosen_copy_count = current; }
-                    else if (sc > sel->lower_score_limit) {
-                        if (sc > score[best]) {                                            /* :1731-1737 (snp counts equal) */
-                            best = enum_idx[k];
-                            if (sc > sel->upper_score_limit) skip_ahead = 1;
+                    if (sc < sel->lower_score_limit && sc > score[best]) {                 /* :1717-1722 */
+                        best = enum_idx[k]; best_snp = m.snp; chosen_masked_arm_proportion = current_masked; chosen_copy_count = current;
+                    } else if (sc > sel->lower_score_limit) {
+                        if (m.snp < best_snp) {                                            /* :1725-1730 */
+                            best = enum_idx[k]; best_snp = m.snp; chosen_masked_arm_proportion = current_masked; chosen_copy_count = current;
+                        } else if (m.snp == best_snp) {                                    /* :1731-1737 */
+                            if (sc > score[best]) {
+                                best = enum_idx[k];
+                                if (sc > sel->upper_score_limit) skip_ahead = 1;
+                            }
                         }
                     }
                 }
@@ -709,16 +757,22 @@ void orc_collapse(const orc_region *r, const orc_cfg *c, const orc_sel *sel, con
     /* mipgen.cpp:1617-1649 */
     int nscan = orc_n_scan(r, c), npos = orc_n_positions(r, c), s0 = orc_first_scan_start(r, c);
     for (long i = 0; i < 2L * npos; i++) pos_best[i] = -1;
+    int *pos_snp = (int *)calloc((size_t)(2L * npos + 1), sizeof(int));
     for (int si = 0; si < nscan; si++)
         for (int strand = 0; strand < 2; strand++) {
             long cur = scan_best[2L * si + strand];
             if (cur < 0) continue;
             orc_dec d; decode_idx(r, c, cur, &d);
-            if (d.ext_copy * d.lig_copy > sel->max_arm_copy || d.ext_copy > sel->target_arm_copy || d.lig_copy > sel->target_arm_copy) continue;
+            if (d.ext_copy * d.lig_copy > sel->max_arm_copy || d.ext_copy > sel->target_arm_copy || d.lig_copy > sel->target_arm_copy) continue;  /* :1628 */
+            orc_selmip m; sel_fields(r, c, sel, &d, &m);
+            if (m.masked > sel->masked_arm_threshold) continue;                            /* :1629 */
             for (int pos = d.s; pos <= d.scan_stop; pos++) {
                 long *slot = &pos_best[2L * (pos - s0) + strand];
-                if (*slot < 0) *slot = cur;
-                else if (score[cur] > score[*slot]) *slot = cur;
+                int *ssnp = &pos_snp[2L * (pos - s0) + strand];
+                if (*slot < 0) { *slot = cur; *ssnp = m.snp; }                             /* :1634-1637 */
+                else if (m.snp < *ssnp) { *slot = cur; *ssnp = m.snp; }                    /* :1638-1641 */
+                else if (score[cur] > score[*slot] && m.snp == *ssnp) { *slot = cur; *ssnp = m.snp; }  /* :1642-1645 */
             }
         }
+    free(pos_snp);
 }

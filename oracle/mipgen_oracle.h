@@ -117,12 +117,20 @@ long orc_tile_replay(const orc_region *r, const orc_cfg *c, const unsigned char 
                      long *out_idx, long cap);
 
 /* ---- selection front-end: best MIP per scan start / per position ---------- */
-/* The knobs of condense_mips / collapse_mips (mipgen.cpp:197-198, 264-265, 177).  Masking (TRF) and SNP
- * inputs are not modelled: arm_fraction_masked = 0 and snp_count = 0, as in every run without -trf and
- * -snp_file (the defaults), and mapping_failed = '0' (stub bwa / unique capture sites). */
+/* The knobs of condense_mips / collapse_mips (mipgen.cpp:197-198, 264-265, 177) and the selection-only inputs
+ * design_mip reads besides the sequence (mipgen.cpp:606-625, 634-760):
+ *   masked_seq   masked_chromosomal_sequence (seq_len chars; NULL => the sequence itself, as with -trf off,
+ *                mipgen.cpp:1058-1062)                                   -> arm_fraction_masked
+ *   snp          [seq_len] non-zero where chr_snp_positions has an entry  -> snp_count
+ *   unmappable   [n_captures][seq_len] non-zero where unmappable_positions[capture][chr] holds that MIP start
+ *                (NULL also stands for -check_copy_number off)            -> mapping_failed */
 typedef struct {
     double lower_score_limit, upper_score_limit;
     int max_arm_copy, target_arm_copy;
+    double masked_arm_threshold;
+    const char *masked_seq;
+    const unsigned char *snp;
+    const unsigned char *unmappable;
 } orc_sel;
 
 /* Positions the region's candidates can cover: [orc_first_scan_start, stop_flanked + max_capture - min_sum - 1] */

@@ -1,14 +1,35 @@
 #!/bin/bash
-# Stand-in for `bwa` so the MIPgen CLI (reference and drop-in alike) runs on a box
+# Stand-in for `bwa` so the MIPgen CLI (reference, drop-in and batched alike) runs on a box
 # without BWA.  mipgen requires `bwa` with no arguments to exit 1 (mipgen.cpp:146-151);
-# `aln` output is ignored; `samse <index> <sai> <fq>` must print one SAM record per
-# read carrying X0:i:1 / X1:i:0 so every capture site maps uniquely and every arm has
-# copy number 1 (mipgen.cpp:581-587, 857).
+# `aln` output is ignored; `samse <index> <sai> <fq>` must print one SAM record per read.
+#
+# Default: every read carries X0:i:1 / X1:i:0, so every capture site maps uniquely and every
+# arm has copy number 1 (mipgen.cpp:581-587, 857).
+# MIPGEN_STUB_RULES=1 switches on deterministic, coordinate-keyed exceptions (mirrored by
+# tests/stub_rules.py) so that copy tables and unmappable MIP starts are exercised:
+#   arm reads      "chr<c>:<start>-<stop>"   k = (31*start + stop - start) % 97
+#                                            X0 = 101 (k==0), 30 (k==1), 3 (k<5), 2 (k<9), else 1
+#   capture reads  "<size>_<c>_<start>"      X0 = 2 when (start + size) % 53 == 0 (ambiguous site)
 [ $# -eq 0 ] && exit 1
 case "$1" in
   aln) exit 0 ;;
   samse)
-    awk 'NR%4==1{n=substr($0,2)} NR%4==2{printf "%s\t0\tchr1\t1\t37\t%dM\t*\t0\t0\t%s\t*\tXT:A:U\tNM:i:0\tX0:i:1\tX1:i:0\n", n, length($0), $0}' "$4"
+    awk -v rules="${MIPGEN_STUB_RULES:-0}" '
+      NR%4==1 { n = substr($0, 2) }
+      NR%4==2 {
+        x0 = 1
+        if (rules == 1) {
+          if (n ~ /^chr/) {
+            split(n, a, ":"); split(a[2], b, "-"); start = b[1] + 0; stop = b[2] + 0
+            k = (31 * start + stop - start) % 97
+            x0 = (k == 0) ? 101 : (k == 1) ? 30 : (k < 5) ? 3 : (k < 9) ? 2 : 1
+          } else {
+            m = split(n, a, "_"); size = a[1] + 0; start = a[m] + 0
+            if ((start + size) % 53 == 0) x0 = 2
+          }
+        }
+        printf "%s\t0\tchr1\t1\t37\t%dM\t*\t0\t0\t%s\t*\tXT:A:U\tNM:i:0\tX0:i:%d\tX1:i:0\n", n, length($0), $0, x0
+      }' "$4"
     exit 0 ;;
 esac
 exit 1

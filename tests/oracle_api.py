@@ -45,7 +45,8 @@ class CRegion(C.Structure):
 
 class CSel(C.Structure):
     _fields_ = [("lower_score_limit", C.c_double), ("upper_score_limit", C.c_double), ("max_arm_copy", C.c_int),
-                ("target_arm_copy", C.c_int)]
+                ("target_arm_copy", C.c_int), ("masked_arm_threshold", C.c_double), ("masked_seq", C.c_char_p),
+                ("snp", c_ubyte_p), ("unmappable", c_ubyte_p)]
 
 
 class CCfg(C.Structure):
@@ -224,11 +225,16 @@ class Oracle(_Lib):
 
 
     def select(self, r: Region, cfg: Config, score: np.ndarray, enum_idx: np.ndarray, lower: float, upper: float,
-               max_arm_copy: int = 75, target_arm_copy: int = 20):
-        """condense_mips + collapse_mips: (scan_best[n_scan,2], pos_best[n_pos,2]) as grid indices (-1: none)."""
+               max_arm_copy: int = 75, target_arm_copy: int = 20, masked_arm_threshold: float = 0.5):
+        """condense_mips + collapse_mips: (scan_best[n_scan,2], pos_best[n_pos,2]) as grid indices (-1: none).
+        The region's masked_seq / snp / unmappable (if any) feed arm_fraction_masked / snp_count / mapping_failed."""
         keep = _Keep()
         cr, cc = c_region(r, keep), c_cfg(cfg, keep)
-        sel = CSel(lower, upper, max_arm_copy, target_arm_copy)
+        snp = np.ascontiguousarray(r.snp, np.uint8) if getattr(r, "snp", None) is not None else None
+        unm = np.ascontiguousarray(r.unmappable, np.uint8) if getattr(r, "unmappable", None) is not None else None
+        keep.refs += [snp, unm]
+        sel = CSel(lower, upper, max_arm_copy, target_arm_copy, masked_arm_threshold, getattr(r, "masked_seq", None),
+                   _np_ptr(snp, c_ubyte_p), _np_ptr(unm, c_ubyte_p))
         score = np.ascontiguousarray(score, dtype=np.float64)
         enum_idx = np.ascontiguousarray(enum_idx, dtype=np.int64)
         n_scan = cfg.n_scan(r)

@@ -20,6 +20,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from mipgen_b200 import panel
 from helpers import small_config, calibrated_model, tmpdir, GOLDEN_DIR
 from cli_util import run_cli, read_rows, REF_CLI
+import stub_rules
 
 CASES = {
     # name: (cli flags, method, lower, upper, config)
@@ -29,7 +30,24 @@ CASES = {
     "svr_2cap": (["-min_capture_size", "157", "-max_capture_size", "162", "-score_method", "svr", "-svr_optimal_score", "0.728",
                   "-svr_priority_score", "0.6", "-arm_length_sums", "40,45"], 1, 0.6, 0.728, small_config((40, 45), 162, 157, 5)),
 }
+# cases that run against the rule-driven stubs (oracle/stub_bwa.sh with MIPGEN_STUB_RULES=1, stub_trf.sh, stub_tabix.sh):
+# arm copy numbers other than 1, ambiguously mapping MIP starts, TRF-masked arms and SNPs in arms -- the selection-only
+# inputs of condense_mips / collapse_mips (mipgen.cpp:1629, 1634-1645, 1689-1737)
+STUB_CASES = {
+    "logistic_stubs_2cap": (["-min_capture_size", "157", "-max_capture_size", "162", "-logistic_optimal_score", "0.9",
+                             "-logistic_priority_score", "0.8", "-arm_length_sums", "40,45", "-trf", "trf"], 0, 0.8, 0.9,
+                            small_config((40, 45), 162, 157, 5)),
+    "svr_stubs_1cap": (["-min_capture_size", "162", "-max_capture_size", "162", "-score_method", "svr", "-svr_optimal_score", "0.728",
+                        "-svr_priority_score", "0.6", "-arm_length_sums", "41,44", "-trf", "trf", "-masked_arm_threshold", "0.3"],
+                       1, 0.6, 0.728, small_config((41, 44), 162, 162, 5)),
+}
+CASES.update(STUB_CASES)
 GENOME_SEED, REGION_SEED, N_REGIONS = 8101, 8102, 2
+
+
+def masked_threshold(case):
+    flags = CASES[case][0]
+    return float(flags[flags.index("-masked_arm_threshold") + 1]) if "-masked_arm_threshold" in flags else 0.5
 
 
 def inputs(oracle, cfg):
@@ -69,7 +87,7 @@ def digest(rows):
             "tail": [list(x) for x in rows[-5:]]}
 
 
-def oracle_rows(oracle, cfg, regions, model, method, lower, upper):
+def oracle_rows(oracle, cfg, regions, model, method, lower, upper, masked_thr=0.5):
     """What the reference writes to all_mips.txt and collapsed_mips.txt, according to the oracle."""
     h = oracle.svm_load_model(model) if method == 1 else None
     all_rows, col_rows = [], []
@@ -78,7 +96,7 @@ def oracle_rows(oracle, cfg, regions, model, method, lower, upper):
         score = sv if method == 1 else lo
         enum_idx = oracle.tile_replay(r, cfg, valid, score, method, True, upper)
         all_rows += [(key_of(cfg, r, int(i)), "%g" % score[i]) for i in enum_idx]
-        _sb, pb = oracle.select(r, cfg, score, enum_idx, lower, upper)
+        _sb, pb = oracle.select(r, cfg, score, enum_idx, lower, upper, masked_arm_threshold=masked_thr)
         for pos in range(pb.shape[0]):
             for strand in (0, 1):
                 if pb[pos, strand] >= 0:
@@ -97,7 +115,13 @@ def reference_rows(case, d, model):
     regions = panel.make_regions(genome, N_REGIONS, 120, 170, cfg, REGION_SEED)
     bed = os.path.join(d, case + ".bed")
     panel.write_bed(bed, regions)
-    run, _log = run_cli(REF_CLI, d, "ref_" + case, bed, gdir, flags, model)
+    env = None
+    if case in STUB_CASES:
+        vcf = os.path.join(d, case + ".vcf")
+        stub_rules.write_vcf(vcf, stub_rules.snp_positions(genome, regions))
+        flags = flags + ["-snp_file", vcf]
+        env = {"MIPGEN_STUB_RULES": "1"}
+    run, _log = run_cli(REF_CLI, d, "ref_" + case, bed, gdir, flags, model, env_extra=env)
     return read_rows(os.path.join(run, "p.all_mips.txt")), read_rows(os.path.join(run, "p.collapsed_mips.txt"))
 
 
@@ -113,12 +137,21 @@ def test_oracle_selection_matches_golden_from_reference_cli(oracle, case):
     _flags, method, lower, upper, cfg = CASES[case]
     d = tmpdir()
     model = model_for(oracle, d)
-    _genome, regions = inputs(oracle, cfg)
-    all_rows, col_rows = oracle_rows(oracle, cfg, regions, model, method, lower, upper)
+    genome, regions = inputs(oracle, cfg)
+    if case in STUB_CASES:
+        stub_rules.decorate(cfg, genome, regions, snps=stub_rules.snp_positions(genome, regions))
+    all_rows, col_rows = oracle_rows(oracle, cfg, regions, model, method, lower, upper, masked_threshold(case))
     assert digest(all_rows) == g["all"], "enumeration order / replay / scores differ from the reference's all_mips.txt"
     assert digest(col_rows) == g["collapsed"], "condense+collapse differ from the reference's collapsed_mips.txt"
-    n_valid = sum(int(oracle.grid_region(r, cfg, None)[0].sum()) for r in regions)
-    assert g["all"]["n"] < n_valid * 0.97, "the case must exercise the score-dependent pruning"
+    if case in STUB_CASES:
+        # the selection-only inputs must matter: without them condense/collapse pick different MIPs
+        for r in regions:
+            r.masked_seq = r.snp = r.unmappable = None
+        _a, plain = oracle_rows(oracle, cfg, regions, model, method, lower, upper, masked_threshold(case))
+        assert digest(plain) != g["collapsed"]
+    else:
+        n_valid = sum(int(oracle.grid_region(r, cfg, None)[0].sum()) for r in regions)
+        assert g["all"]["n"] < n_valid * 0.97, "the case must exercise the score-dependent pruning"
 
 
 @pytest.mark.skipif(not os.path.exists(REF_CLI), reason="oracle/_ref/mipgen not built (needs /root/reference)")
