@@ -270,7 +270,7 @@ typedef struct {
     double *logistic;
     double *svr;
 } mg_tile_result;
-/* Prefix sums a caller needs to size mg_tile_result (pure host arithmetic): grid points, scan starts and coverable
+/* Prefix sums a caller needs to size the arrays of mg_tile_result -- pure host arithmetic: grid points, scan starts and coverable
  * positions of regions[0..n); each array has n + 1 entries and may be NULL. */
 int mg_tile_sizes(const mg_config *cfg, const mg_region *regions, int n, int64_t *grid_off, int64_t *scan_off, int64_t *pos_off);
 /* want: MG_WANT_LOGISTIC and/or MG_WANT_SVR (what to score); sp selects on sp->method's scores (mixed = logistic,

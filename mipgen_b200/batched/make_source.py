@@ -1,0 +1,45 @@
+#!/usr/bin/env python3
+"""Build-time source transformation for the batched MIPgen driver (INTEGRATION.md route C).
+
+    python make_source.py /root/reference/mipgen.cpp _build/mipgen_batched.cpp
+
+Reads the reference's mipgen.cpp WHERE IT LIES and writes a patched copy into the (git-ignored) build directory; nothing
+of the reference is stored in this repository.  Three anchored edits, each checked to match exactly once:
+
+  1. `#include "mipgen_batched.h"` before `class mipgen{`, `#include "batched_members.inc"` right after its `public:`;
+  2. tile_regions (mipgen.cpp:403-556): the statements from the initialisation of current_scan_start_position (:421)
+     through `collapse_mips();` (:505) become `b200_tile_feature(feature);`;
+  3. predict_value (mipgen.cpp:1948): first statement returns the device score parked by get_parameters, if any.
+"""
+import re
+import sys
+
+
+def one(pattern, text, what, flags=0):
+    m = list(re.finditer(pattern, text, flags))
+    if len(m) != 1:
+        sys.exit("make_source.py: anchor for %s matched %d times (reference changed?)" % (what, len(m)))
+    return m[0]
+
+
+def main():
+    src, dst = sys.argv[1], sys.argv[2]
+    t = open(src, encoding="latin-1", newline="").read()
+    # 1. includes
+    m = one(r"class\s+mipgen\s*\{\s*\n\s*public:\s*\n", t, "class mipgen")
+    t = t[:m.start()] + '#include "mipgen_batched.h"\n' + t[m.start():m.end()] + '#include "batched_members.inc"\n' + t[m.end():]
+    # 2. the candidate loop nest + condense + collapse of one feature
+    a = one(r"^[ \t]*feature->current_scan_start_position\s*=\s*feature->start_position_flanked\s*-\s*max_capture_size[^\n]*\n", t,
+            "start of the tile loop", re.M)
+    b = one(r"^[ \t]*collapse_mips\(\);[^\n]*\n", t, "collapse_mips() call", re.M)
+    if not (a.start() < b.start()):
+        sys.exit("make_source.py: tile loop anchors out of order")
+    t = t[:a.start()] + "\t\tb200_tile_feature(feature); // mipgen_b200: loop nest + condense_mips + collapse_mips on the GPU\n" + t[b.end():]
+    # 3. predict_value
+    m = one(r"double\s+predict_value\s*\(\s*vector<double>\s*&\s*parameters\s*,\s*svm_model\s*\*\s*model\s*\)\s*\{", t, "predict_value")
+    t = t[:m.end()] + "\n\t{ double b200_score; if (mipgen_b200_take_pending_svr(&b200_score)) return b200_score; } // mipgen_b200\n" + t[m.end():]
+    open(dst, "w", encoding="latin-1", newline="").write(t)
+
+
+if __name__ == "__main__":
+    main()

@@ -38,6 +38,11 @@ class SVMipv4
     vector<int> snp_positions;
     string snp_ext_sequence, snp_lig_sequence, snp_mip_sequence;
 
+    // batched driver only (mipgen_b200/batched): the SVR score the device computed for this candidate, handed to the
+    // caller's predict_value by get_parameters (mixed mode re-scores picked MIPs, mipgen.cpp:1523-1550, 1873-1877)
+    bool b200_has_svr;
+    double b200_svr;
+
     SVMipv4(string chromosome, int scan_start, int scan_stop, int ext_length, int lig_length);
     virtual ~SVMipv4() {}
     virtual int get_mip_start() = 0;

@@ -48,11 +48,15 @@ namespace mgshim {
 
 static mg_ctx *g_ctx = nullptr;
 static bool g_have_model = false;
+static bool g_has_pending_svr = false;  // batched driver: get_parameters -> predict_value hand-over
+static double g_pending_svr = 0;
 
 static mg_ctx *ctx()
 {
     if (!g_ctx) {
+        // MIPGEN_B200_DEVICE=<ordinal>, or the first entry of MIPGEN_B200_DEVICES (batched driver: "0,1,2" / "0-7")
         const char *dev = getenv("MIPGEN_B200_DEVICE");
+        if (!dev || !*dev) dev = getenv("MIPGEN_B200_DEVICES");
         if (mg_create(dev ? atoi(dev) : 0, &g_ctx) != MG_OK) fatal("mg_create", nullptr);
     }
     return g_ctx;
@@ -302,6 +306,19 @@ static long locate(const SVMipv4 *m, bool need_svr, const double *lrc)
 
 }  // namespace mgshim
 
+// entry points of the batched driver (mipgen_b200/batched/mipgen_batched.h)
+mg_ctx *mipgen_b200_shim_context() { return mgshim::ctx(); }
+
+bool mipgen_b200_take_pending_svr(double *score)
+{
+    if (!mgshim::g_has_pending_svr) return false;
+    mgshim::g_has_pending_svr = false;
+    *score = mgshim::g_pending_svr;
+    return true;
+}
+
+[[noreturn]] void mipgen_b200_fatal(const char *what, mg_ctx *c) { mgshim::fatal(what, c); }
+
 // ------------------------------------------------------------------------------------
 // Featurev5
 // ------------------------------------------------------------------------------------
@@ -376,7 +393,7 @@ SVMipv4::SVMipv4(string chromosome, int scan_start, int scan_stop, int ext_lengt
     : chr(chromosome), scan_start_position(scan_start), scan_stop_position(scan_stop), scan_size(scan_stop - scan_start + 1),
       extension_arm_length(ext_length), ligation_arm_length(lig_length), ext_probe_start(0), ext_probe_stop(0), lig_probe_start(0),
       lig_probe_stop(0), ext_probe_copy(0), lig_probe_copy(0), arm_fraction_masked(0), translocation_failed('0'), snp_failed('0'),
-      mapping_failed('0'), masking_failed('0'), snp_count(0), has_snp_mip(false), score(0)
+      mapping_failed('0'), masking_failed('0'), snp_count(0), has_snp_mip(false), score(0), b200_has_svr(false), b200_svr(0)
 {
 }
 
@@ -397,6 +414,13 @@ double SVMipv4::get_score()
 
 void SVMipv4::get_parameters(vector<double> &parameters, double long_range_content[])
 {
+    if (b200_has_svr) {
+        // batched driver: the object was materialised from a device grid and carries its SVR score; the patched
+        // predict_value picks it up instead of round-tripping 192 doubles through text (mipgen.cpp:1948-2019)
+        mgshim::g_pending_svr = b200_svr;
+        mgshim::g_has_pending_svr = true;
+        return;
+    }
     mgshim::Engine &e = mgshim::engine();
     parameters.resize(MG_NFEAT);
     long idx = mgshim::g_have_model ? mgshim::locate(this, true, long_range_content) : -1;

@@ -10,6 +10,8 @@
 #   arm reads      "chr<c>:<start>-<stop>"   k = (31*start + stop - start) % 97
 #                                            X0 = 101 (k==0), 30 (k==1), 3 (k<5), 2 (k<9), else 1
 #   capture reads  "<size>_<c>_<start>"      X0 = 2 when (start + size) % 53 == 0 (ambiguous site)
+# MIPGEN_STUB_RULES=2: the arm rule only (no ambiguous sites: design_mip leaves masking_failed uninitialised after a
+# mapping failure, mipgen.cpp:622-624, so all_mips.txt of such a run is not reproducible even by the reference itself)
 [ $# -eq 0 ] && exit 1
 case "$1" in
   aln) exit 0 ;;
@@ -18,12 +20,12 @@ case "$1" in
       NR%4==1 { n = substr($0, 2) }
       NR%4==2 {
         x0 = 1
-        if (rules == 1) {
+        if (rules == 1 || rules == 2) {
           if (n ~ /^chr/) {
             split(n, a, ":"); split(a[2], b, "-"); start = b[1] + 0; stop = b[2] + 0
             k = (31 * start + stop - start) % 97
             x0 = (k == 0) ? 101 : (k == 1) ? 30 : (k < 5) ? 3 : (k < 9) ? 2 : 1
-          } else {
+          } else if (rules == 1) {
             m = split(n, a, "_"); size = a[1] + 0; start = a[m] + 0
             if ((start + size) % 53 == 0) x0 = 2
           }

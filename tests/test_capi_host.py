@@ -129,3 +129,37 @@ def test_lpt_sharding_is_a_partition_and_balanced():
         assert flat == list(range(61))
         loads = [sum(costs[i] for i in o) for o in owned]
         assert max(loads) - min(loads) <= max(costs)
+
+
+def test_tile_sizes_and_partition_are_host_arithmetic():
+    """mg_tile_sizes / mg_partition_regions need no device: prefix sums match the Python config arithmetic, the partition is a
+    deterministic longest-processing-time assignment that covers every region once and balances the grid sizes."""
+    cfg = panel.Config(170, 150, 5)
+    genome = panel.lcg_genome(panel.genome_length_for(23, 400, cfg), 12)
+    regions = panel.make_regions(genome, 23, 60, 400, cfg, 13)
+    g, s, p = mg.tile_sizes(cfg, regions)
+    assert [int(x) for x in np.diff(g)] == [cfg.grid_size(r) for r in regions]
+    assert [int(x) for x in np.diff(s)] == [cfg.n_scan(r) for r in regions]
+    min_sum = min(e + l for e, l in zip(cfg.ext_len, cfg.lig_len))
+    assert [int(x) for x in np.diff(p)] == [r.stop_flanked + cfg.max_capture - min_sum - 1 - cfg.first_scan_start(r) + 1 for r in regions]
+    for parts in (1, 2, 3, 8):
+        owner = mg.partition_regions(cfg, regions, parts)
+        assert owner.min() >= 0 and owner.max() < parts and owner.size == len(regions)
+        load = np.bincount(owner, weights=np.diff(g), minlength=parts)
+        assert load.max() - load.min() <= np.diff(g).max()          # LPT bound
+        assert np.array_equal(owner, mg.partition_regions(cfg, regions, parts))
+        assert np.array_equal(owner, np.array([next(k for k, o in enumerate(shard.lpt_assign(list(np.diff(g)), parts)) if i in o)
+                                               for i in range(len(regions))]))
+
+
+def test_config_rejects_misordered_arm_pairs():
+    """The replay of the tile loop's skips relies on pairs grouped by arm sum, sums descending (mipgen.cpp:431-438)."""
+    ok = panel.Config()
+    assert mg.config_grid_size(ok, _one_region(ok)) > 0
+    bad = panel.Config(ext_len=[16, 20, 17], lig_len=[24, 25, 23])  # sums 40, 45, 40
+    assert mg.config_grid_size(bad, _one_region(bad)) == -1
+
+
+def _one_region(cfg):
+    genome = panel.lcg_genome(8000, 3)
+    return panel.cut_region(genome, 3001, 3100, cfg)

@@ -22,6 +22,10 @@ from cli_util import REF_CLI, run_cli  # noqa: E402
 from helpers import tmpdir  # noqa: E402
 import test_selection_pinning as sp  # noqa: E402
 
+# records with failure flags other than "000" need design_mip's SNP / masking logic: the stub-rule cases are out of the
+# formatter's scope (it refuses such regions)
+PLAIN_CASES = [c for c in sp.CASES if c not in sp.STUB_CASES]
+
 GOLDEN_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 HEADER = (">mip_key\t%s_score\tchr\text_probe_start\text_probe_stop\text_probe_copy\text_probe_sequence\tlig_probe_start\t"
           "lig_probe_stop\tlig_probe_copy\tlig_probe_sequence\tmip_scan_start_position\tmip_scan_stop_position\t"
@@ -56,7 +60,7 @@ def oracle():
     return Oracle()
 
 
-@pytest.mark.parametrize("case", sorted(sp.CASES))
+@pytest.mark.parametrize("case", sorted(PLAIN_CASES))
 def test_records_from_oracle_scores_equal_reference_files(oracle, case):
     g = json.load(open(os.path.join(GOLDEN_DIR, "records_%s.json" % case)))
     _flags, method, lower, upper, cfg = sp.CASES[case]
@@ -119,7 +123,7 @@ def test_describe_candidates_geometry_copies_and_errors(oracle):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("case", sorted(sp.CASES))
+@pytest.mark.parametrize("case", sorted(PLAIN_CASES))
 def test_records_from_device_scores_equal_reference_files(oracle, case):
     g = json.load(open(os.path.join(GOLDEN_DIR, "records_%s.json" % case)))
     _flags, method, lower, upper, cfg = sp.CASES[case]
@@ -150,7 +154,7 @@ def test_records_from_device_scores_equal_reference_files(oracle, case):
 
 
 @pytest.mark.skipif(not os.path.exists(REF_CLI), reason="oracle/_ref/mipgen not built (needs /root/reference)")
-@pytest.mark.parametrize("case", sorted(sp.CASES))
+@pytest.mark.parametrize("case", sorted(PLAIN_CASES))
 def test_golden_is_what_the_reference_cli_writes(oracle, case):
     assert reference_files(oracle, case) == json.load(open(os.path.join(GOLDEN_DIR, "records_%s.json" % case)))
 
@@ -174,7 +178,7 @@ def reference_files(oracle, case):
 if __name__ == "__main__":
     from oracle_api import Oracle
     o = Oracle()
-    for case in sorted(sp.CASES):
+    for case in sorted(PLAIN_CASES):
         g = reference_files(o, case)
         json.dump(g, open(os.path.join(GOLDEN_DIR, "records_%s.json" % case), "w"), indent=1)
         print(case, g)
