@@ -112,6 +112,7 @@ typedef struct {
     double svr_dmma;  /* DMMA.8x8x4 warp instructions (256 FP64 FMA each)                    */
     double svr_exp;   /* kernel values exp(-gamma d) evaluated                               */
     double svr_gather;/* factor triples multiplied and accumulated (factored form only)      */
+    double svr_tc_mma;/* tcgen05.mma instructions (M128 N64 K16, FP16 in / FP32 out) of the tensor-core form */
 } mg_timings;
 
 /* ---- context ---------------------------------------------------------------- */
@@ -138,8 +139,12 @@ int mg_set_svr_model(mg_ctx *ctx, const double *sv, const double *alpha, int n_s
 int mg_model_info(const mg_ctx *ctx, int *n_sv, double *gamma, double *rho);
 /* How region grids are SVR-scored: 0 = automatic (the factored kernel when the arm-pair table
  * fits its shared-memory tables, else the dense contraction), 1 = dense DMMA contraction,
- * 2 = factored (error if it does not fit).  Both compute the same FP64 decision value. */
+ * 2 = factored (error if it does not fit).  Those compute the same FP64 decision value.
+ * 3 = the tcgen05 tensor-core form: split-FP16 contraction with FP32 TMEM accumulators, FP64 exponent /
+ * exp / row sum (k_svr_tc.cu); ~1e-9 relative to libsvm instead of ~1e-13, see DESIGN.md.  Error if the
+ * model's length / junction columns are not small integers (mg_svr_tensor_core_available). */
 int mg_set_svr_mode(mg_ctx *ctx, int mode);
+int mg_svr_tensor_core_available(const mg_ctx *ctx);
 /* > 0 (the factored kernel's window size) if the current config fits the factored kernel */
 int mg_svr_factored_available(const mg_ctx *ctx);
 /* svm_predict for n dense rows x[i*ld .. i*ld+191] (features 1..192). out[n]. */

@@ -63,7 +63,7 @@ class MgTimings(C.Structure):
     _fields_ = [("ms_feat", C.c_double), ("launches_feat", C.c_long), ("ms_svr", C.c_double),
                 ("launches_svr", C.c_long), ("ms_other", C.c_double), ("launches_other", C.c_long),
                 ("candidates_feat", C.c_long), ("candidates_svr", C.c_long),
-                ("svr_dmma", C.c_double), ("svr_exp", C.c_double), ("svr_gather", C.c_double)]
+                ("svr_dmma", C.c_double), ("svr_exp", C.c_double), ("svr_gather", C.c_double), ("svr_tc_mma", C.c_double)]
 
 
 # every symbol include/mipgen_b200.h declares: (name, restype, argtypes)
@@ -82,6 +82,7 @@ SYMBOLS = [
     ("mg_set_svr_model", C.c_int, [C.c_void_p, c_double_p, c_double_p, C.c_int, C.c_int, C.c_double, C.c_double]),
     ("mg_set_svr_mode", C.c_int, [C.c_void_p, C.c_int]),
     ("mg_svr_factored_available", C.c_int, [C.c_void_p]),
+    ("mg_svr_tensor_core_available", C.c_int, [C.c_void_p]),
     ("mg_model_info", C.c_int, [C.c_void_p, c_int_p, c_double_p, c_double_p]),
     ("mg_svr_predict", C.c_int, [C.c_void_p, c_double_p, C.c_long, C.c_long, c_double_p]),
     ("mg_svr_predict_direct", C.c_int, [C.c_void_p, c_double_p, C.c_long, C.c_long, c_double_p]),
@@ -419,11 +420,14 @@ class Context:
                                               sv.shape[1], gamma, rho))
 
     def set_svr_mode(self, mode: int) -> None:
-        """0 auto, 1 dense DMMA contraction, 2 factored."""
+        """0 auto, 1 dense DMMA contraction, 2 factored, 3 tensor cores (tcgen05, split FP16)."""
         self._check(self.lib.mg_set_svr_mode(self.h, mode))
 
     def svr_factored_available(self) -> int:
         return int(self.lib.mg_svr_factored_available(self.h))
+
+    def svr_tensor_core_available(self) -> bool:
+        return bool(self.lib.mg_svr_tensor_core_available(self.h))
 
     def model_info(self):
         n, g, r = C.c_int(), C.c_double(), C.c_double()

@@ -1,0 +1,499 @@
+// k_svr_tc.cu -- K-svr on the 5th-generation tensor cores (tcgen05 / TMEM), split-precision form.
+//
+//   score(x) = sum_i alpha_i * exp(-gamma * ||x - s_i||^2) - rho        (svm.cpp:2504-2522, 328-368)
+//
+// tcgen05.mma has no FP64 kind, so the candidates x support-vectors contraction is recast so that the tensor cores
+// only ever see numbers they represent EXACTLY and FP32 accumulation errors stay ~1e-8 absolute on a quantity that
+// enters the exponent multiplied by 2*gamma (~1e-2):
+//
+//   * the 127 fractional feature columns (k-mer frequencies: ext 1..21, insert 67..151, lig 153..173) are centred on
+//     the support vectors' column means (RBF kernels are translation invariant; |x'| ~ 0.05) and split into two FP16
+//     terms  x' = hi + 2^-11 * lo  (22 significant bits; the lo term is pre-scaled so it stays a normal FP16 number):
+//         x'.s' ~= hi.hi' + 2^-11 * (hi.lo' + lo.hi')       three K=128 kind::f16 MMAs, two FP32 TMEM accumulators
+//   * the integer-valued columns (arm lengths 22 / 174, scan size 152, junction one-hot 175..190), centred on integers,
+//     are exact in FP16 (|v| <= 2048) and their products sum exactly in FP32 (< 2^24): a third accumulator, K=32;
+//   * the copy-number columns (191, 192) are zero unless BWA found extra copies: an FP64 correction per row that has them;
+//   * the long-range block (23..66) is constant per region: it rides in the per-SV weight, as in the factored kernel;
+//   * ||x'||^2, ||s'||^2 are FP64 (row constant R, per-SV weight), the exponent is assembled and exponentiated in FP64
+//     (the 10-instruction exp of k_svr.cu) and the row sums are FP64.
+// Measured deviation from libsvm's double arithmetic: see profiles/ (bench.py `tensor_core_kernel`); the FP64 kernels
+// (k_svr.cu, k_svr_fact.cu) remain the default and the reference for it.
+//
+// CTA = one tile of 128 candidates of ONE region x all support vectors, 12 warps:
+//   all      build the A operand once: rows read from K-feat's feature matrix, centred, split, written K-major with the
+//            128-byte swizzle the tensor core expects (hand-applied: the operand is computed, not copied, so no TMA
+//            tensor map), fence.proxy.async;
+//   warp 0   one lane streams per-64-SV operand images (pre-swizzled at model upload: ONE 41 KB cp.async.bulk + the
+//            region's weights) through a 3-stage mbarrier ring;
+//   warp 1   one lane issues the tcgen05.mma chain of a tile (8 + 16 + 2 instructions, M128 N64 K16) into one of two TMEM
+//            accumulator stages and commits to the smem-empty / accumulator-full barriers;
+//   warps 4-11  epilogue: tcgen05.ld (thread = candidate row, 16 columns at a time), FP32 recombination, FP64 exponent,
+//            exp, weight, row sum; two column halves per row are added at the end.
+#include <cuda_fp16.h>
+
+#include "mg_common.cuh"
+
+namespace {
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t *bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
+{
+    uint32_t done;
+    do {
+        asm volatile(
+            "{\n"
+            ".reg .pred p;\n"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+            "selp.u32 %0, 1, 0, p;\n"
+            "}\n"
+            : "=r"(done)
+            : "r"(smem_u32(bar)), "r"(parity)
+            : "memory");
+    } while (!done);
+}
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+// tcgen05.commit: the mbarrier gets one arrival when every tcgen05.mma issued so far by this thread has completed
+__device__ __forceinline__ void umma_commit(uint64_t *bar)
+{
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// K-major operand, SWIZZLE_128B: 8-row x 128-byte atoms, 1024 bytes apart (tools/probe_tcgen05.cu checks this encoding)
+__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr)
+{
+    uint64_t d = (uint64_t)((saddr & 0x3FFFFu) >> 4);
+    d |= (uint64_t)(1024u >> 4) << 32;  // stride between 8-row groups
+    d |= (uint64_t)1 << 46;             // descriptor version (sm_100)
+    d |= (uint64_t)2 << 61;             // SWIZZLE_128B
+    return d;
+}
+__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate)
+{
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(tmem_d),
+        "l"(da), "l"(db), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16])
+{
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]), "=r"(v[10]),
+          "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+        : "r"(taddr)
+        : "memory");
+}
+
+// exp of N exponents at once, stage by stage (same table and polynomial as exp_nonpos in k_svr.cu).  Exponents are
+// clamped to >= -708 on the high word (magnitudes of negative doubles order like unsigned ints); positive ones pass.
+template <int N>
+__device__ __forceinline__ void expn(double (&t)[N], const double *__restrict__ tab64)
+{
+    const double kMagic = 6755399441055744.0;
+    double kf0[N], r[N], q[N];
+#pragma unroll
+    for (int i = 0; i < N; i++) t[i] = __hiloint2double((int)min((unsigned)__double2hiint(t[i]), 0xC0862000u), __double2loint(t[i]));
+#pragma unroll
+    for (int i = 0; i < N; i++) kf0[i] = fma(t[i], 92.332482616893657, kMagic);
+#pragma unroll
+    for (int i = 0; i < N; i++) q[i] = kf0[i] - kMagic;
+#pragma unroll
+    for (int i = 0; i < N; i++) r[i] = fma(q[i], -0x1.62e42fee00000p-7, t[i]);
+#pragma unroll
+    for (int i = 0; i < N; i++) r[i] = fma(q[i], -0x1.a39ef35793c76p-39, r[i]);
+#pragma unroll
+    for (int i = 0; i < N; i++) q[i] = fma(r[i], 1.0 / 120.0, 1.0 / 24.0);
+#pragma unroll
+    for (int i = 0; i < N; i++) q[i] = fma(q[i], r[i], 1.0 / 6.0);
+#pragma unroll
+    for (int i = 0; i < N; i++) q[i] = fma(q[i], r[i], 0.5);
+#pragma unroll
+    for (int i = 0; i < N; i++) r[i] = fma(r[i] * r[i], q[i], r[i]);
+#pragma unroll
+    for (int i = 0; i < N; i++) {
+        const int k = __double2loint(kf0[i]);
+        const double tj = tab64[k & 63];
+        const double v = fma(tj, r[i], tj);
+        t[i] = __hiloint2double(__double2hiint(v) + ((k >> 6) << 20), __double2loint(v));
+    }
+}
+
+constexpr int kThreads = TC_THREADS;
+constexpr int kEpiWarp0 = 4, kEpiWarps = 8;
+constexpr uint32_t kTmemCols = 512;  // 2 accumulator stages x (hi.hi | cross | integer) x 64 columns = 384 -> next power of two
+
+// shared-memory carve-up (bytes from the 1024-aligned base)
+constexpr int kOffAhi = 0, kOffAlo = TC_A_F_BYTES, kOffAI = 2 * TC_A_F_BYTES, kOffB = 2 * TC_A_F_BYTES + TC_A_I_BYTES;
+constexpr int kOffRow = kOffB + TC_STAGES * TC_STAGE_BYTES;             // R[128], xce[128], xcl[128], part[128] doubles
+constexpr int kOffTab = kOffRow + 4 * TC_M * 8;                         // exp table [64] doubles
+constexpr int kOffBar = kOffTab + 64 * 8;                               // 10 mbarriers
+constexpr int kOffMisc = kOffBar + 16 * 8;                              // tmem base, row state[128] ints
+constexpr int kSmemBytes = kOffMisc + 16 + TC_M * 4 + 1024;             // + slack for the 1024-byte alignment of the base
+
+// byte offset of element (row, k) in a K-major FP16 tile of `rows` rows: K blocks of 64 columns (128 bytes) are separate
+// [rows x 128 B] panels; inside a panel 8-row atoms of 1024 bytes, 16-byte chunks XOR-swizzled with the row
+__host__ __device__ inline uint32_t tc_sw128(int rows, int row, int k)
+{
+    const int kb = k >> 6, kk = k & 63;
+    const uint32_t chunk = (uint32_t)(kk >> 3) ^ (uint32_t)(row & 7);
+    return (uint32_t)kb * (uint32_t)rows * 128u + (uint32_t)(row >> 3) * 1024u + (uint32_t)(row & 7) * 128u + chunk * 16u + (uint32_t)(kk & 7) * 2u;
+}
+
+// fractional column k (0..126) of the A/B operands -> feature index (0-based) of the 192-vector
+__host__ __device__ inline int tc_frac_feature(int k) { return k < 21 ? k : (k < 106 ? 66 + (k - 21) : 152 + (k - 106)); }
+// integer column k (0..18): ext_len, scan_size, lig_len, junction one-hot
+__host__ __device__ inline int tc_int_feature(int k) { return k == 0 ? 21 : (k == 1 ? 151 : (k == 2 ? 173 : 174 + (k - 3))); }
+
+__global__ void __launch_bounds__(kThreads, 1)
+k_svr_tc(const DevRegion *__restrict__ regions, const int64_t *__restrict__ tile_off, const int *__restrict__ tile_region, int n_spans,
+         const double *__restrict__ x, int64_t g_base, const uint8_t *__restrict__ valid, const uint8_t *__restrict__ b_img,
+         const double *__restrict__ w_all, const double *__restrict__ centre, const double *__restrict__ exp2_tab, int n_sv_pad,
+         double gamma, double rho, double zero_score, double *__restrict__ out)
+{
+    extern __shared__ uint8_t smem_unaligned[];
+    uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_unaligned) + 1023) & ~(uintptr_t)1023);
+    double *rowR = reinterpret_cast<double *>(smem + kOffRow), *rowCe = rowR + TC_M, *rowCl = rowCe + TC_M, *part = rowCl + TC_M;
+    double *etab = reinterpret_cast<double *>(smem + kOffTab);
+    uint64_t *bars = reinterpret_cast<uint64_t *>(smem + kOffBar);
+    uint64_t *b_full = bars, *b_empty = bars + 3, *d_full = bars + 6, *d_empty = bars + 8;
+    uint32_t *tmem_base_s = reinterpret_cast<uint32_t *>(smem + kOffMisc);
+    int *rowState = reinterpret_cast<int *>(smem + kOffMisc + 16);  // 0 skipped, 1 invalid (zero row), 2 scored, 3 non-finite feature
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+
+    // which span (region x chunk) this tile belongs to: spans are few, binary search on their tile prefix sums
+    int lo = 0, hi = n_spans - 1;
+    while (lo < hi) {
+        const int mid = (lo + hi + 1) >> 1;
+        if (tile_off[2 * mid] <= (int64_t)blockIdx.x) lo = mid; else hi = mid - 1;
+    }
+    const int region = tile_region[lo];
+    const int64_t g0 = tile_off[2 * lo + 1] + ((int64_t)blockIdx.x - tile_off[2 * lo]) * TC_M;   // first candidate of the tile
+    const int64_t g_end = tile_off[2 * lo + 1] + tile_off[2 * n_spans + lo];                       // end of the span
+    const int n_rows = (int)(g_end - g0 < (int64_t)TC_M ? g_end - g0 : (int64_t)TC_M);
+    const double *w_reg = w_all + (int64_t)region * n_sv_pad;
+    const int n_tiles = n_sv_pad / TC_N;
+
+    if (tid < 64) etab[tid] = exp2_tab[tid];
+    if (tid == 0) {
+        for (int s = 0; s < TC_STAGES; s++) { mbar_init(&b_full[s], 1); mbar_init(&b_empty[s], 1 + kEpiWarps); }
+        for (int s = 0; s < 2; s++) { mbar_init(&d_full[s], 1); mbar_init(&d_empty[s], kEpiWarps); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 2) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_base_s)), "r"(kTmemCols) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+
+    // ---- A operand: one warp per row; lanes over the columns.  Integer-block tile is cleared first (its K is padded). ----
+    for (int i = tid; i < TC_A_I_BYTES / 16; i += kThreads) reinterpret_cast<int4 *>(smem + kOffAI)[i] = make_int4(0, 0, 0, 0);
+    __syncthreads();
+    for (int row = warp; row < TC_M; row += kThreads / 32) {
+        const int64_t g = g0 + row;
+        const bool in = row < n_rows;
+        const uint8_t vd = in ? valid[g] : 0;
+        const double *xr = x + (g - g_base) * MG_NFEAT;
+        double ssum = 0.0;
+#pragma unroll
+        for (int m = 0; m < 4; m++) {
+            const int k = lane + 32 * m;
+            double v = 0.0;
+            if (vd && k < TC_KF_USED) v = xr[tc_frac_feature(k)] - centre[k];
+            const __half h = __double2half(v);
+            const __half l = __double2half((v - (double)__half2float(h)) * 2048.0);
+            *reinterpret_cast<__half *>(smem + kOffAhi + tc_sw128(TC_M, row, k)) = h;
+            *reinterpret_cast<__half *>(smem + kOffAlo + tc_sw128(TC_M, row, k)) = l;
+            ssum = fma(v, v, ssum);
+        }
+        double f22 = 0.0, ce = 0.0, cl = 0.0;
+        if (lane < TC_KI_USED) {
+            double v = 0.0;
+            if (vd) {
+                const double raw = xr[tc_int_feature(lane)];
+                if (lane == 0) f22 = raw;
+                v = raw - centre[TC_KF + lane];
+            }
+            *reinterpret_cast<__half *>(smem + kOffAI + tc_sw128(TC_M, row, lane)) = __double2half(v);  // small integers: exact
+            ssum = fma(v, v, ssum);
+        } else if (lane == TC_KI_USED && vd) {
+            ce = xr[190]; cl = xr[191];  // log10 copy numbers (0 for copy 1); -inf for copy 0
+            ssum = fma(ce, ce, fma(cl, cl, ssum));
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) ssum += __shfl_xor_sync(0xffffffffu, ssum, o);
+        f22 = __shfl_sync(0xffffffffu, f22, 0);
+        ce = __shfl_sync(0xffffffffu, ce, TC_KI_USED);
+        cl = __shfl_sync(0xffffffffu, cl, TC_KI_USED);
+        if (lane == 0) {
+            const bool finite = fabs(ssum) <= 1.7976931348623157e308;
+            rowState[row] = !vd ? 0 : (f22 == 0.0 ? 1 : (finite ? 2 : 3));
+            rowR[row] = finite ? -gamma * ssum : 0.0;
+            rowCe[row] = finite ? 2.0 * gamma * ce : 0.0;
+            rowCl[row] = finite ? 2.0 * gamma * cl : 0.0;
+        }
+    }
+    // generic-proxy writes of the operand -> visible to the tensor core (async proxy); TMEM address -> everyone
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_d = *tmem_base_s;
+
+    if (warp == 0) {
+        // ======================= producer: SV operand images + the region's weights =======================
+        if (lane == 0) {
+            for (int j = 0; j < n_tiles; j++) {
+                const int s = j % TC_STAGES;
+                if (j >= TC_STAGES) mbar_wait(&b_empty[s], ((j / TC_STAGES) - 1) & 1);
+                uint8_t *dst = smem + kOffB + s * TC_STAGE_BYTES;
+                mbar_arrive_expect_tx(&b_full[s], TC_IMG_BYTES + TC_N * 8);
+                bulk_g2s(dst, b_img + (size_t)j * TC_IMG_BYTES, TC_IMG_BYTES, &b_full[s]);
+                bulk_g2s(dst + TC_IMG_BYTES, w_reg + (size_t)j * TC_N, TC_N * 8, &b_full[s]);
+            }
+        }
+    } else if (warp == 1) {
+        // ======================= MMA issuer =======================
+        if (lane == 0) {
+            // D = F32, A = B = F16, both K-major, N >> 3 at [17,23), M >> 4 at [24,29)
+            const uint32_t idesc = (1u << 4) | ((uint32_t)(TC_N >> 3) << 17) | ((uint32_t)(TC_M >> 4) << 24);
+            const uint32_t a_hi = smem_u32(smem + kOffAhi), a_lo = smem_u32(smem + kOffAlo), a_i = smem_u32(smem + kOffAI);
+            for (int j = 0; j < n_tiles; j++) {
+                const int s = j % TC_STAGES, ds = j & 1;
+                mbar_wait(&b_full[s], (j / TC_STAGES) & 1);
+                if (j >= 2) mbar_wait(&d_empty[ds], ((j >> 1) - 1) & 1);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const uint32_t b_hi = smem_u32(smem + kOffB + s * TC_STAGE_BYTES), b_lo = b_hi + TC_B_F_BYTES, b_i = b_hi + 2 * TC_B_F_BYTES;
+                const uint32_t d_hh = tmem_d + (uint32_t)(ds * 3 * TC_N), d_x = d_hh + TC_N, d_i = d_hh + 2 * TC_N;
+#pragma unroll
+                for (int ks = 0; ks < TC_KF / 16; ks++) {  // K block of 64 columns = one 128-byte swizzle row; 4 steps of 32 bytes inside
+                    const uint32_t ao = (uint32_t)(ks >> 2) * (TC_M * 128) + (uint32_t)(ks & 3) * 32, bo = (uint32_t)(ks >> 2) * (TC_N * 128) + (uint32_t)(ks & 3) * 32;
+                    umma_f16(d_hh, umma_desc(a_hi + ao), umma_desc(b_hi + bo), idesc, ks > 0);
+                }
+#pragma unroll
+                for (int ks = 0; ks < TC_KF / 16; ks++) {
+                    const uint32_t ao = (uint32_t)(ks >> 2) * (TC_M * 128) + (uint32_t)(ks & 3) * 32, bo = (uint32_t)(ks >> 2) * (TC_N * 128) + (uint32_t)(ks & 3) * 32;
+                    umma_f16(d_x, umma_desc(a_hi + ao), umma_desc(b_lo + bo), idesc, ks > 0);
+                }
+#pragma unroll
+                for (int ks = 0; ks < TC_KF / 16; ks++) {
+                    const uint32_t ao = (uint32_t)(ks >> 2) * (TC_M * 128) + (uint32_t)(ks & 3) * 32, bo = (uint32_t)(ks >> 2) * (TC_N * 128) + (uint32_t)(ks & 3) * 32;
+                    umma_f16(d_x, umma_desc(a_lo + ao), umma_desc(b_hi + bo), idesc, 1);
+                }
+#pragma unroll
+                for (int ks = 0; ks < 2; ks++)  // 19 integer columns, padded to 32
+                    umma_f16(d_i, umma_desc(a_i + ks * 32), umma_desc(b_i + ks * 32), idesc, ks > 0);
+                umma_commit(&b_empty[s]);   // the operand stage may be refilled once these MMAs have read it
+                umma_commit(&d_full[ds]);   // ... and the accumulators are complete
+            }
+        }
+    } else if (warp >= kEpiWarp0) {
+        // ======================= epilogue: thread = candidate row (TMEM lane), half of the 64 columns =======================
+        const int q = warp & 3, half = (warp - kEpiWarp0) >> 2, row = q * 32 + lane;
+        const double R = rowR[row], xce = rowCe[row], xcl = rowCl[row];
+        const int state = rowState[row];
+        const bool copies = xce != 0.0 || xcl != 0.0;
+        const double g2 = 2.0 * gamma;
+        double acc = 0.0;
+        for (int j = 0; j < n_tiles; j++) {
+            const int s = j % TC_STAGES, ds = j & 1;
+            mbar_wait(&b_full[s], (j / TC_STAGES) & 1);   // completed long ago; orders our reads of the stage's constants
+            mbar_wait(&d_full[ds], (j >> 1) & 1);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const uint8_t *stage = smem + kOffB + s * TC_STAGE_BYTES;
+            const double *sce = reinterpret_cast<const double *>(stage + 2 * TC_B_F_BYTES + TC_B_I_BYTES), *scl = sce + TC_N;
+            const double *wt = reinterpret_cast<const double *>(stage + TC_IMG_BYTES);
+            const uint32_t t0 = tmem_d + ((uint32_t)(q * 32) << 16) + (uint32_t)(ds * 3 * TC_N + half * 32);
+#pragma unroll
+            for (int c0 = 0; c0 < 32; c0 += 16) {
+                uint32_t vh[16], vx[16], vi[16];
+                tmem_ld16(t0 + c0, vh);
+                tmem_ld16(t0 + TC_N + c0, vx);
+                tmem_ld16(t0 + 2 * TC_N + c0, vi);
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                if (c0 == 16) {
+                    // every TMEM read of this accumulator stage is done: hand it back to the MMA issuer
+                    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&d_empty[ds]);
+                }
+#pragma unroll
+                for (int h8 = 0; h8 < 16; h8 += 8) {
+                    double e[8];
+#pragma unroll
+                    for (int i = 0; i < 8; i++) {
+                        const float f = fmaf(__uint_as_float(vx[h8 + i]), 1.0f / 2048.0f, __uint_as_float(vh[h8 + i]));
+                        const double d = (double)f + (double)__uint_as_float(vi[h8 + i]);
+                        e[i] = fma(d, g2, R);
+                    }
+                    if (copies) {
+#pragma unroll
+                        for (int i = 0; i < 8; i++) {
+                            const int col = half * 32 + c0 + h8 + i;
+                            e[i] = fma(xce, sce[col], fma(xcl, scl[col], e[i]));
+                        }
+                    }
+                    expn<8>(e, etab);
+#pragma unroll
+                    for (int i = 0; i < 8; i++) acc = fma(e[i], wt[half * 32 + c0 + h8 + i], acc);
+                }
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&b_empty[s]);  // constants of the stage are consumed
+        }
+        // the two column halves of a row
+        if (half == 1) part[row] = acc;
+        asm volatile("bar.sync 1, %0;" ::"n"(kEpiWarps * 32) : "memory");
+        if (half == 0 && row < n_rows) {
+            const double total = acc + part[row];
+            const double nan = __longlong_as_double(0x7ff8000000000000LL);
+            out[g0 + row] = state == 2 ? total - rho : (state == 3 ? -rho : (state == 1 ? zero_score : nan));
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 2) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "r"(kTmemCols) : "memory");
+}
+
+// per region r and support vector i:  w'[r][i] = alpha_i * exp(-gamma * (||lrc_r - s_i[23..66]||^2 + tail_i)) * exp(-gamma ||s'_i||^2)
+__global__ void __launch_bounds__(256) k_lrc_weights_tc(const double *__restrict__ lrc_all, const double *__restrict__ sv, const double *__restrict__ alpha,
+                                                        const double *__restrict__ tail, const double *__restrict__ exp_c, int n_sv_pad,
+                                                        double gamma, double *__restrict__ w)
+{
+    __shared__ double l[MG_NLRC];
+    const int r = blockIdx.x;
+    if (threadIdx.x < MG_NLRC) l[threadIdx.x] = lrc_all ? lrc_all[(int64_t)r * MG_NLRC + threadIdx.x] : 0.0;
+    __syncthreads();
+    for (int i = threadIdx.x; i < n_sv_pad; i += blockDim.x) {
+        const double *s = sv + (int64_t)i * MG_NFEAT + 22;
+        double d = tail[i];
+#pragma unroll 4
+        for (int j = 0; j < MG_NLRC; j++) { const double t = l[j] - s[j]; d = fma(t, t, d); }
+        w[(int64_t)r * n_sv_pad + i] = alpha[i] * exp(-gamma * d) * exp_c[i];
+    }
+}
+
+}  // namespace
+
+int launch_tc_setup(mg_ctx *ctx)
+{
+    CUDA_TRY(ctx, cudaFuncSetAttribute(k_svr_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+    return MG_OK;
+}
+
+// Host side of the model upload: centres, FP16 operand images, per-SV constants.  Returns false when the model cannot
+// be represented (integer columns that are not small integers): the tensor-core mode is then unavailable.
+bool mg_tc_prepare_model(const std::vector<double> &sv, int n_sv_pad, int n_sv, double gamma, std::vector<uint8_t> &img,
+                         std::vector<double> &centre, std::vector<double> &exp_c)
+{
+    centre.assign(TC_KF + TC_KI, 0.0);
+    if (n_sv <= 0) return false;
+    for (int k = 0; k < TC_KF_USED; k++) {
+        double m = 0;
+        for (int i = 0; i < n_sv; i++) m += sv[(size_t)i * MG_NFEAT + tc_frac_feature(k)];
+        centre[k] = m / n_sv;
+    }
+    for (int k = 0; k < 3; k++) {  // the three length columns: integer centres; the junction columns stay uncentred
+        double m = 0;
+        for (int i = 0; i < n_sv; i++) m += sv[(size_t)i * MG_NFEAT + tc_int_feature(k)];
+        centre[TC_KF + k] = nearbyint(m / n_sv);
+    }
+    for (int i = 0; i < n_sv; i++)
+        for (int k = 0; k < TC_KI_USED; k++) {
+            const double v = sv[(size_t)i * MG_NFEAT + tc_int_feature(k)] - centre[TC_KF + k];
+            if (v != nearbyint(v) || fabs(v) > 1024.0) return false;
+        }
+    const int n_tiles = n_sv_pad / TC_N;
+    img.assign((size_t)n_tiles * TC_IMG_BYTES, 0);
+    exp_c.assign((size_t)n_sv_pad, 0.0);
+    for (int i = 0; i < n_sv_pad; i++) {
+        uint8_t *t = &img[(size_t)(i / TC_N) * TC_IMG_BYTES];
+        const int r = i % TC_N;
+        const double *s = &sv[(size_t)i * MG_NFEAT];
+        double ss = 0;
+        for (int k = 0; k < TC_KF_USED; k++) {
+            const double v = s[tc_frac_feature(k)] - centre[k];
+            const __half h = __double2half(v);
+            const __half l = __double2half((v - (double)__half2float(h)) * 2048.0);
+            memcpy(t + tc_sw128(TC_N, r, k), &h, 2);
+            memcpy(t + TC_B_F_BYTES + tc_sw128(TC_N, r, k), &l, 2);
+            ss += v * v;
+        }
+        for (int k = 0; k < TC_KI_USED; k++) {
+            const double v = s[tc_int_feature(k)] - centre[TC_KF + k];
+            const __half h = __double2half(i < n_sv ? v : 0.0);
+            memcpy(t + 2 * TC_B_F_BYTES + tc_sw128(TC_N, r, k), &h, 2);
+            if (i < n_sv) ss += v * v;
+        }
+        double *sce = reinterpret_cast<double *>(t + 2 * TC_B_F_BYTES + TC_B_I_BYTES), *scl = sce + TC_N;
+        sce[r] = s[190]; scl[r] = s[191];
+        ss += s[190] * s[190] + s[191] * s[191];
+        exp_c[i] = exp(-gamma * ss);
+    }
+    return true;
+}
+
+int launch_lrc_weights_tc(mg_ctx *ctx, const mg_panel *p, double *d_w)
+{
+    mg_time_begin(ctx, TM_OTHER, p->n_regions);
+    k_lrc_weights_tc<<<p->n_regions, 256, 0, ctx->stream>>>(p->d_lrc, ctx->d_sv, ctx->d_alpha, ctx->d_tail, ctx->d_tc_expc, ctx->n_sv_pad, ctx->gamma, d_w);
+    mg_time_end(ctx);
+    CUDA_TRY(ctx, cudaGetLastError());
+    return MG_OK;
+}
+
+// candidates [g0, g1) of the panel (feature rows at d_x, row g - g0), tiles of 128 that never straddle a region
+int launch_svr_tc(mg_ctx *ctx, const mg_panel *p, const double *d_x, int64_t g0, int64_t g1, const uint8_t *d_valid, const double *d_w, double *d_out)
+{
+    if (g1 <= g0) return MG_OK;
+    // spans = (region x this chunk); arrays: [2*s] first tile, [2*s+1] first candidate, then [2*n + s] length
+    std::vector<int64_t> off;
+    std::vector<int> reg;
+    std::vector<int64_t> len;
+    int64_t tiles = 0;
+    for (int r = 0; r < p->n_regions; r++) {
+        const int64_t a = std::max(g0, p->offsets[r]), b = std::min(g1, p->offsets[r + 1]);
+        if (b <= a) continue;
+        off.push_back(tiles); off.push_back(a);
+        len.push_back(b - a);
+        reg.push_back(r);
+        tiles += (b - a + TC_M - 1) / TC_M;
+    }
+    const int n_spans = (int)reg.size();
+    if (n_spans == 0 || tiles == 0) return MG_OK;
+    if (tiles > 0x7fffffff) { ctx->err = "launch_svr_tc: too many tiles in one launch"; return MG_ERR_INVALID; }
+    off.insert(off.end(), len.begin(), len.end());
+    int64_t *d_off = nullptr;
+    int *d_reg = nullptr;
+    CUDA_TRY(ctx, mg_dev_alloc(ctx, (void **)&d_off, off.size() * 8));
+    CUDA_TRY(ctx, mg_dev_alloc(ctx, (void **)&d_reg, reg.size() * 4));
+    // pageable sources: the copies are staged by the runtime before the call returns
+    CUDA_TRY(ctx, cudaMemcpyAsync(d_off, off.data(), off.size() * 8, cudaMemcpyHostToDevice, ctx->stream));
+    CUDA_TRY(ctx, cudaMemcpyAsync(d_reg, reg.data(), reg.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
+    mg_time_begin(ctx, TM_SVR, g1 - g0);
+    k_svr_tc<<<(unsigned)tiles, kThreads, kSmemBytes, ctx->stream>>>(p->d_regions, d_off, d_reg, n_spans, d_x, g0, d_valid, ctx->d_tc_img, d_w,
+                                                                    ctx->d_tc_centre, ctx->d_exp2tab, ctx->n_sv_pad, ctx->gamma, ctx->rho,
+                                                                    ctx->zero_score, d_out);
+    mg_time_end(ctx);
+    CUDA_TRY(ctx, cudaGetLastError());
+    mg_dev_free(ctx, d_off);
+    mg_dev_free(ctx, d_reg);
+    ctx->tm.svr_tc_mma += (double)tiles * (ctx->n_sv_pad / TC_N) * 26.0;
+    return MG_OK;
+}

@@ -260,7 +260,7 @@ extern "C" int mg_create(int device, mg_ctx **out)
         lc[i] = (uint8_t)code;
     }
     if (mg_upload_lrc_tables(ctx, lk, lc) != MG_OK || launch_svr_setup(ctx) != MG_OK || launch_feat_setup(ctx) != MG_OK ||
-        launch_fact_setup(ctx) != MG_OK) {
+        launch_fact_setup(ctx) != MG_OK || launch_tc_setup(ctx) != MG_OK) {
         g_create_err = ctx->err;
         delete ctx;
         return MG_ERR_CUDA;
@@ -273,6 +273,9 @@ static void free_model(mg_ctx *ctx)
 {
     cudaFree(ctx->d_fact_blob);
     ctx->d_fact_blob = nullptr;
+    cudaFree(ctx->d_tc_img); cudaFree(ctx->d_tc_centre); cudaFree(ctx->d_tc_expc);
+    ctx->d_tc_img = nullptr; ctx->d_tc_centre = ctx->d_tc_expc = nullptr;
+    ctx->tc_ok = false;
     cudaFree(ctx->d_sv); cudaFree(ctx->d_sv_tiled); cudaFree(ctx->d_ss); cudaFree(ctx->d_alpha); cudaFree(ctx->d_tail);
     ctx->d_sv = ctx->d_sv_tiled = ctx->d_ss = ctx->d_alpha = ctx->d_tail = nullptr;
     ctx->has_model = false;
@@ -529,6 +532,20 @@ static int upload_model(mg_ctx *ctx, const std::vector<double> &dense, const std
         CUDA_TRY(ctx, cudaMalloc(&ctx->d_fact_blob, blob.size() * 8));
         CUDA_TRY(ctx, cudaMemcpy(ctx->d_fact_blob, blob.data(), blob.size() * 8, cudaMemcpyHostToDevice));
     }
+    // tensor-core kernel: centred FP16 hi/lo operand images (k_svr_tc.cu)
+    {
+        std::vector<uint8_t> img;
+        std::vector<double> centre, exp_c;
+        ctx->tc_ok = mg_tc_prepare_model(sv, pad, n_sv, gamma, img, centre, exp_c);
+        if (ctx->tc_ok) {
+            CUDA_TRY(ctx, cudaMalloc(&ctx->d_tc_img, img.size()));
+            CUDA_TRY(ctx, cudaMemcpy(ctx->d_tc_img, img.data(), img.size(), cudaMemcpyHostToDevice));
+            CUDA_TRY(ctx, cudaMalloc(&ctx->d_tc_centre, centre.size() * 8));
+            CUDA_TRY(ctx, cudaMemcpy(ctx->d_tc_centre, centre.data(), centre.size() * 8, cudaMemcpyHostToDevice));
+            CUDA_TRY(ctx, cudaMalloc(&ctx->d_tc_expc, exp_c.size() * 8));
+            CUDA_TRY(ctx, cudaMemcpy(ctx->d_tc_expc, exp_c.data(), exp_c.size() * 8, cudaMemcpyHostToDevice));
+        }
+    }
     ctx->n_sv = n_sv; ctx->n_sv_pad = pad; ctx->gamma = gamma; ctx->rho = rho;
     ctx->has_model = true;
     // SVR value of the all-zero vector (what an invalid candidate scores, SVMipv4.cpp:63-68), from the dense kernel
@@ -616,10 +633,12 @@ extern "C" int mg_load_svr_model(mg_ctx *ctx, const char *path)
 
 extern "C" int mg_set_svr_mode(mg_ctx *ctx, int mode)
 {
-    if (!ctx || mode < 0 || mode > 2) return MG_ERR_INVALID;
+    if (!ctx || mode < 0 || mode > 3) return MG_ERR_INVALID;
     ctx->svr_mode = mode;
     return MG_OK;
 }
+
+extern "C" int mg_svr_tensor_core_available(const mg_ctx *ctx) { return ctx && ctx->has_model && ctx->tc_ok; }
 
 extern "C" int mg_svr_factored_available(const mg_ctx *ctx) { return ctx && ctx->fact_ok ? ctx->fact_W : 0; }
 
@@ -820,7 +839,7 @@ extern "C" void mg_panel_destroy(mg_panel *p)
     if (!p) return;
     cudaSetDevice(p->ctx->device);
     mg_ctx *c = p->ctx;
-    mg_dev_free(c, p->d_ftasks); mg_dev_free(c, p->d_w);
+    mg_dev_free(c, p->d_ftasks); mg_dev_free(c, p->d_w); mg_dev_free(c, p->d_w_tc);
     mg_dev_free(c, p->d_regions); mg_dev_free(c, p->d_tasks); mg_dev_free(c, p->d_codes); mg_dev_free(c, p->d_lrc); mg_dev_free(c, p->d_copies);
     mg_dev_free(c, p->d_maskpf); mg_dev_free(c, p->d_snppf); mg_dev_free(c, p->d_unmap);
     mg_dev_free(c, p->d_valid); mg_dev_free(c, p->d_logistic); mg_dev_free(c, p->d_svr); mg_dev_free(c, p->d_feat);
@@ -1011,8 +1030,23 @@ extern "C" int mg_panel_score(mg_ctx *ctx, mg_panel *p, int want)
     }
     int rc = MG_OK;
     const int n_win = (int)p->h_windows.size(), n_tasks = (int)p->h_tasks.size();
+    // tensor-core form on request (mode 3)
+    const bool tc = w_svr && ctx->svr_mode == 3;
+    if (tc) {
+        if (!ctx->tc_ok || ctx->cfg.max_capture > 1024) {
+            ctx->err = "tensor-core SVR requested but the model's length / junction columns (or the capture sizes) are not small integers";
+            return MG_ERR_INVALID;
+        }
+        if (!p->d_w_tc || p->w_tc_n_sv_pad != ctx->n_sv_pad) {
+            mg_dev_free(ctx, p->d_w_tc);
+            p->d_w_tc = nullptr;
+            CUDA_TRY(ctx, mg_dev_alloc(ctx, (void **)&p->d_w_tc, (size_t)p->n_regions * ctx->n_sv_pad * 8));
+            p->w_tc_n_sv_pad = ctx->n_sv_pad;
+        }
+        if ((rc = launch_lrc_weights_tc(ctx, p, p->d_w_tc)) != MG_OK) return rc;
+    }
     // factored SVR when the configuration fits its tables (mode 0/2); dense otherwise (mode 1, or as fallback)
-    const bool fact = w_svr && ctx->svr_mode != 1 && ctx->fact_ok && !p->h_ftasks.empty();
+    const bool fact = w_svr && !tc && ctx->svr_mode != 1 && ctx->fact_ok && !p->h_ftasks.empty();
     if (w_svr && ctx->svr_mode == 2 && !fact) {
         ctx->err = "factored SVR requested but the configuration does not fit its shared-memory tables";
         return MG_ERR_INVALID;
@@ -1028,6 +1062,7 @@ extern "C" int mg_panel_score(mg_ctx *ctx, mg_panel *p, int want)
     }
     // windows [w0, w1) <-> candidates [g0, g1)
     auto svr_range = [&](int w0, int w1, const double *xbuf, int64_t g0, int64_t g1) {
+        if (tc) return launch_svr_tc(ctx, p, xbuf, g0, g1, p->d_valid, p->d_w_tc, p->d_svr);
         if (fact) return launch_svr_fact(ctx, p, p->ftask_start[w0], p->ftask_start[w1], xbuf, g0, g1 - g0, p->d_valid, p->d_w, p->d_svr);
         return launch_svr(ctx, xbuf, g1 - g0, p->d_valid + g0, p->d_svr + g0);
     };

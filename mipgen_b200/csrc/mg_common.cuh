@@ -128,6 +128,24 @@ __host__ __device__ inline uint32_t fd_pack(uint32_t kind, uint32_t part, uint32
 #define FACT_MAX_LEN 64
 #define FACT_MAX_SPAN 128
 
+// ---------------------------------------------------------------------------
+// tensor-core SVR (k_svr_tc.cu): tile shape and operand images
+// ---------------------------------------------------------------------------
+#define TC_M 128           // candidates per CTA tile (= TMEM lanes)
+#define TC_N 64            // support vectors per MMA tile
+#define TC_KF 128          // fractional columns (127 used), FP16 hi / lo
+#define TC_KF_USED 127
+#define TC_KI 64           // integer columns, padded to one 128-byte operand row (19 used, 32 multiplied)
+#define TC_KI_USED 19
+#define TC_STAGES 3
+#define TC_THREADS 384
+#define TC_A_F_BYTES (2 * TC_M * 128)      // two K blocks of 64 FP16 columns x 128 rows
+#define TC_A_I_BYTES (TC_M * 128)
+#define TC_B_F_BYTES (2 * TC_N * 128)
+#define TC_B_I_BYTES (TC_N * 128)
+#define TC_IMG_BYTES (2 * TC_B_F_BYTES + TC_B_I_BYTES + 2 * TC_N * 8)   // hi | lo | integer | s_191[64] | s_192[64]
+#define TC_STAGE_BYTES 43008               // image + the region's 64 weights, rounded up to a multiple of 1024
+
 struct DevFact {
     int n_pairs, n_cap, n_ext, n_lig, n_sums, min_sum, max_sum, W;
     int cap_FA, cap_FQ, cap_FI, cap_R;   // shared-memory capacities in doubles / rows
@@ -187,6 +205,11 @@ struct mg_ctx {
     DevFact h_fact{};               // host copy (work accounting)
     double *d_fact_blob = nullptr;  // [n_sv_pad/FACT_C][FACT_BLOB] per-chunk SV blocks + block norms
     double zero_score = 0;          // SVR value of the all-zero vector (invalid candidates)
+    // tensor-core SVR (svr_mode 3)
+    bool tc_ok = false;             // the model's integer columns are small integers: representable exactly in FP16
+    uint8_t *d_tc_img = nullptr;    // [n_sv_pad / TC_N][TC_IMG_BYTES] pre-swizzled operand images
+    double *d_tc_centre = nullptr;  // [TC_KF + TC_KI] column centres
+    double *d_tc_expc = nullptr;    // [n_sv_pad] exp(-gamma ||s'||^2)
     // workspace
     double *d_x = nullptr;      // feature rows of the chunk in flight
     size_t x_rows_cap = 0;
@@ -220,6 +243,8 @@ struct mg_panel {
     DevFTask *d_ftasks = nullptr;
     double *d_w = nullptr;              // [n_regions][n_sv_pad] alpha * exp(-g d_lrc)
     int w_n_sv_pad = 0;
+    double *d_w_tc = nullptr;           // the same times exp(-g ||s'||^2): per-SV weights of the tensor-core kernel
+    int w_tc_n_sv_pad = 0;
     int span_cap = 0, pf_stride = 0;
     uint8_t *d_codes = nullptr;
     int64_t n_codes = 0;
@@ -284,4 +309,11 @@ int launch_lrc_weights(mg_ctx *ctx, const mg_panel *p, double *d_w);
 int launch_svr_fact(mg_ctx *ctx, const mg_panel *p, int ftask0, int ftask1, const double *d_x, int64_t g_base, int64_t n_cand,
                     const uint8_t *d_valid, const double *d_w, double *d_out);
 int mg_upload_lrc_tables(mg_ctx *ctx, const uint8_t *k, const uint8_t *code);
+// tensor-core SVR (k_svr_tc.cu)
+int launch_tc_setup(mg_ctx *ctx);
+bool mg_tc_prepare_model(const std::vector<double> &sv, int n_sv_pad, int n_sv, double gamma, std::vector<uint8_t> &img,
+                         std::vector<double> &centre, std::vector<double> &exp_c);
+int launch_lrc_weights_tc(mg_ctx *ctx, const mg_panel *p, double *d_w);
+int launch_svr_tc(mg_ctx *ctx, const mg_panel *p, const double *d_x, int64_t g0, int64_t g1, const uint8_t *d_valid, const double *d_w,
+                  double *d_out);
 int launch_svr_direct(mg_ctx *ctx, const double *d_x, int64_t n, int64_t ld, double *d_out);

@@ -17,6 +17,7 @@ from mipgen_b200 import panel  # noqa: E402
 def main():
     n_regions = int(sys.argv[1]) if len(sys.argv) > 1 else 8
     passes = int(sys.argv[2]) if len(sys.argv) > 2 else 2
+    mode = int(sys.argv[3]) if len(sys.argv) > 3 else 0   # mg_set_svr_mode: 0 factored, 1 dense, 3 tensor cores
     cfg = panel.Config()
     ctx = mg.Context(0)
     ctx.set_config(cfg)
@@ -25,6 +26,7 @@ def main():
     for r in regions:
         r.lrc = ctx.long_range_content(r.flank_seq, r.seq_start, r.seq_stop)
     pnl = ctx.panel(regions)
+    ctx.set_svr_mode(mode)
     for _ in range(passes):
         pnl.score(mg.MG_WANT_SVR)
     pnl.score(mg.MG_WANT_LOGISTIC)
