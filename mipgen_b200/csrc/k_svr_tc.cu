@@ -19,7 +19,7 @@
 // Measured deviation from libsvm's double arithmetic: see profiles/ (bench.py `tensor_core_kernel`); the FP64 kernels
 // (k_svr.cu, k_svr_fact.cu) remain the default and the reference for it.
 //
-// CTA = one tile of 128 candidates of ONE region x all support vectors, 12 warps:
+// CTA = one tile of 128 candidates of ONE region x all support vectors, 20 warps:
 //   all      build the A operand once: rows read from K-feat's feature matrix, centred, split, written K-major with the
 //            128-byte swizzle the tensor core expects (hand-applied: the operand is computed, not copied, so no TMA
 //            tensor map), fence.proxy.async;
@@ -27,8 +27,11 @@
 //            region's weights) through a 3-stage mbarrier ring;
 //   warp 1   one lane issues the tcgen05.mma chain of a tile (8 + 16 + 2 instructions, M128 N64 K16) into one of two TMEM
 //            accumulator stages and commits to the smem-empty / accumulator-full barriers;
-//   warps 4-11  epilogue: tcgen05.ld (thread = candidate row, 16 columns at a time), FP32 recombination, FP64 exponent,
-//            exp, weight, row sum; two column halves per row are added at the end.
+//   warps 4-19  epilogue: tcgen05.ld (thread = candidate row, 8 columns at a time; four warps per TMEM lane quarter share the
+//            64 columns), FP32 recombination, FP64 exponent, exp, weight, row sum; the four partial sums of a row are added
+//            at the end.  The FP64 pipe is the busiest unit of this kernel and it is latency bound at low occupancy, hence
+//            four epilogue warps per scheduler and a 7-instruction exp (256-entry 2^(j/256) table, degree-3 polynomial:
+//            |r| <= ln2/512, r^4/24 < 1.4e-13 -- two orders below the operand split's own error).
 #include <cuda_fp16.h>
 
 #include "mg_common.cuh"
@@ -91,59 +94,52 @@ __device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t da, uint64_t 
         "l"(da), "l"(db), "r"(idesc), "r"(accumulate)
         : "memory");
 }
-__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16])
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t (&v)[8])
 {
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
-        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]), "=r"(v[10]),
-          "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
-        : "r"(taddr)
-        : "memory");
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
+                 : "r"(taddr)
+                 : "memory");
 }
 
-// exp of N exponents at once, stage by stage (same table and polynomial as exp_nonpos in k_svr.cu).  Exponents are
-// clamped to >= -708 on the high word (magnitudes of negative doubles order like unsigned ints); positive ones pass.
+// exp of N exponents at once, stage by stage: t = (256 n + j) ln2/256 + r, exp(t) = 2^n * 2^(j/256) * (1 + r + r^2/2 + r^3/6).
+// Exponents are clamped to >= -708 on the high word (magnitudes of negative doubles order like unsigned ints); positive
+// ones (the per-SV weight carries the matching negative part) pass unchanged.
 template <int N>
-__device__ __forceinline__ void expn(double (&t)[N], const double *__restrict__ tab64)
+__device__ __forceinline__ void expn(double (&t)[N], const double *__restrict__ tab256)
 {
     const double kMagic = 6755399441055744.0;
     double kf0[N], r[N], q[N];
 #pragma unroll
     for (int i = 0; i < N; i++) t[i] = __hiloint2double((int)min((unsigned)__double2hiint(t[i]), 0xC0862000u), __double2loint(t[i]));
 #pragma unroll
-    for (int i = 0; i < N; i++) kf0[i] = fma(t[i], 92.332482616893657, kMagic);
+    for (int i = 0; i < N; i++) kf0[i] = fma(t[i], 369.32993046757463, kMagic);   // 256 / ln2
 #pragma unroll
     for (int i = 0; i < N; i++) q[i] = kf0[i] - kMagic;
 #pragma unroll
-    for (int i = 0; i < N; i++) r[i] = fma(q[i], -0x1.62e42fee00000p-7, t[i]);
+    for (int i = 0; i < N; i++) r[i] = fma(q[i], -0.0027076061740622863, t[i]);   // ln2 / 256 (|q| < 2^19: one constant is enough)
 #pragma unroll
-    for (int i = 0; i < N; i++) r[i] = fma(q[i], -0x1.a39ef35793c76p-39, r[i]);
-#pragma unroll
-    for (int i = 0; i < N; i++) q[i] = fma(r[i], 1.0 / 120.0, 1.0 / 24.0);
-#pragma unroll
-    for (int i = 0; i < N; i++) q[i] = fma(q[i], r[i], 1.0 / 6.0);
-#pragma unroll
-    for (int i = 0; i < N; i++) q[i] = fma(q[i], r[i], 0.5);
+    for (int i = 0; i < N; i++) q[i] = fma(r[i], 1.0 / 6.0, 0.5);
 #pragma unroll
     for (int i = 0; i < N; i++) r[i] = fma(r[i] * r[i], q[i], r[i]);
 #pragma unroll
     for (int i = 0; i < N; i++) {
         const int k = __double2loint(kf0[i]);
-        const double tj = tab64[k & 63];
+        const double tj = tab256[k & 255];
         const double v = fma(tj, r[i], tj);
-        t[i] = __hiloint2double(__double2hiint(v) + ((k >> 6) << 20), __double2loint(v));
+        t[i] = __hiloint2double(__double2hiint(v) + ((k >> 8) << 20), __double2loint(v));
     }
 }
 
 constexpr int kThreads = TC_THREADS;
-constexpr int kEpiWarp0 = 4, kEpiWarps = 8;
+constexpr int kEpiWarp0 = 4, kEpiWarps = 16;
 constexpr uint32_t kTmemCols = 512;  // 2 accumulator stages x (hi.hi | cross | integer) x 64 columns = 384 -> next power of two
 
 // shared-memory carve-up (bytes from the 1024-aligned base)
 constexpr int kOffAhi = 0, kOffAlo = TC_A_F_BYTES, kOffAI = 2 * TC_A_F_BYTES, kOffB = 2 * TC_A_F_BYTES + TC_A_I_BYTES;
-constexpr int kOffRow = kOffB + TC_STAGES * TC_STAGE_BYTES;             // R[128], xce[128], xcl[128], part[128] doubles
-constexpr int kOffTab = kOffRow + 4 * TC_M * 8;                         // exp table [64] doubles
-constexpr int kOffBar = kOffTab + 64 * 8;                               // 10 mbarriers
+constexpr int kOffRow = kOffB + TC_STAGES * TC_STAGE_BYTES;             // R[128], xce[128], xcl[128], part[3][128] doubles
+constexpr int kOffTab = kOffRow + 6 * TC_M * 8;                         // exp table [256] doubles
+constexpr int kOffBar = kOffTab + 256 * 8;                              // 10 mbarriers
 constexpr int kOffMisc = kOffBar + 16 * 8;                              // tmem base, row state[128] ints
 constexpr int kSmemBytes = kOffMisc + 16 + TC_M * 4 + 1024;             // + slack for the 1024-byte alignment of the base
 
@@ -169,7 +165,7 @@ k_svr_tc(const DevRegion *__restrict__ regions, const int64_t *__restrict__ tile
 {
     extern __shared__ uint8_t smem_unaligned[];
     uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_unaligned) + 1023) & ~(uintptr_t)1023);
-    double *rowR = reinterpret_cast<double *>(smem + kOffRow), *rowCe = rowR + TC_M, *rowCl = rowCe + TC_M, *part = rowCl + TC_M;
+    double *rowR = reinterpret_cast<double *>(smem + kOffRow), *rowCe = rowR + TC_M, *rowCl = rowCe + TC_M, *part = rowCl + TC_M;  // part[3][TC_M]
     double *etab = reinterpret_cast<double *>(smem + kOffTab);
     uint64_t *bars = reinterpret_cast<uint64_t *>(smem + kOffBar);
     uint64_t *b_full = bars, *b_empty = bars + 3, *d_full = bars + 6, *d_empty = bars + 8;
@@ -191,7 +187,7 @@ k_svr_tc(const DevRegion *__restrict__ regions, const int64_t *__restrict__ tile
     const double *w_reg = w_all + (int64_t)region * n_sv_pad;
     const int n_tiles = n_sv_pad / TC_N;
 
-    if (tid < 64) etab[tid] = exp2_tab[tid];
+    if (tid < 256) etab[tid] = exp2_tab[tid];
     if (tid == 0) {
         for (int s = 0; s < TC_STAGES; s++) { mbar_init(&b_full[s], 1); mbar_init(&b_empty[s], 1 + kEpiWarps); }
         for (int s = 0; s < 2; s++) { mbar_init(&d_full[s], 1); mbar_init(&d_empty[s], kEpiWarps); }
@@ -205,48 +201,57 @@ k_svr_tc(const DevRegion *__restrict__ regions, const int64_t *__restrict__ tile
     // ---- A operand: one warp per row; lanes over the columns.  Integer-block tile is cleared first (its K is padded). ----
     for (int i = tid; i < TC_A_I_BYTES / 16; i += kThreads) reinterpret_cast<int4 *>(smem + kOffAI)[i] = make_int4(0, 0, 0, 0);
     __syncthreads();
-    for (int row = warp; row < TC_M; row += kThreads / 32) {
-        const int64_t g = g0 + row;
-        const bool in = row < n_rows;
-        const uint8_t vd = in ? valid[g] : 0;
-        const double *xr = x + (g - g_base) * MG_NFEAT;
-        double ssum = 0.0;
+    // four rows per warp and step, so that their (latency-bound) global loads overlap
+    constexpr int kRB = 4;
+    for (int rb = warp * kRB; rb < TC_M; rb += (kThreads / 32) * kRB) {
+        double vf[kRB][4], vi[kRB], vce[kRB], vcl[kRB];
+        uint8_t vd[kRB];
 #pragma unroll
-        for (int m = 0; m < 4; m++) {
-            const int k = lane + 32 * m;
-            double v = 0.0;
-            if (vd && k < TC_KF_USED) v = xr[tc_frac_feature(k)] - centre[k];
-            const __half h = __double2half(v);
-            const __half l = __double2half((v - (double)__half2float(h)) * 2048.0);
-            *reinterpret_cast<__half *>(smem + kOffAhi + tc_sw128(TC_M, row, k)) = h;
-            *reinterpret_cast<__half *>(smem + kOffAlo + tc_sw128(TC_M, row, k)) = l;
-            ssum = fma(v, v, ssum);
-        }
-        double f22 = 0.0, ce = 0.0, cl = 0.0;
-        if (lane < TC_KI_USED) {
-            double v = 0.0;
-            if (vd) {
-                const double raw = xr[tc_int_feature(lane)];
-                if (lane == 0) f22 = raw;
-                v = raw - centre[TC_KF + lane];
+        for (int j = 0; j < kRB; j++) {
+            const int row = rb + j;
+            const int64_t g = g0 + row;
+            vd[j] = row < n_rows ? valid[g] : 0;
+            const double *xr = x + (g - g_base) * MG_NFEAT;
+#pragma unroll
+            for (int m = 0; m < 4; m++) {
+                const int k = lane + 32 * m;
+                vf[j][m] = (vd[j] && k < TC_KF_USED) ? xr[tc_frac_feature(k)] : 0.0;
             }
-            *reinterpret_cast<__half *>(smem + kOffAI + tc_sw128(TC_M, row, lane)) = __double2half(v);  // small integers: exact
-            ssum = fma(v, v, ssum);
-        } else if (lane == TC_KI_USED && vd) {
-            ce = xr[190]; cl = xr[191];  // log10 copy numbers (0 for copy 1); -inf for copy 0
-            ssum = fma(ce, ce, fma(cl, cl, ssum));
+            vi[j] = (vd[j] && lane < TC_KI_USED) ? xr[tc_int_feature(lane)] : 0.0;
+            vce[j] = (vd[j] && lane == TC_KI_USED) ? xr[190] : 0.0;  // log10 copy numbers (0 for copy 1; -inf for copy 0)
+            vcl[j] = (vd[j] && lane == TC_KI_USED) ? xr[191] : 0.0;
         }
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) ssum += __shfl_xor_sync(0xffffffffu, ssum, o);
-        f22 = __shfl_sync(0xffffffffu, f22, 0);
-        ce = __shfl_sync(0xffffffffu, ce, TC_KI_USED);
-        cl = __shfl_sync(0xffffffffu, cl, TC_KI_USED);
-        if (lane == 0) {
-            const bool finite = fabs(ssum) <= 1.7976931348623157e308;
-            rowState[row] = !vd ? 0 : (f22 == 0.0 ? 1 : (finite ? 2 : 3));
-            rowR[row] = finite ? -gamma * ssum : 0.0;
-            rowCe[row] = finite ? 2.0 * gamma * ce : 0.0;
-            rowCl[row] = finite ? 2.0 * gamma * cl : 0.0;
+        for (int j = 0; j < kRB; j++) {
+            const int row = rb + j;
+            double ssum = 0.0;
+#pragma unroll
+            for (int m = 0; m < 4; m++) {
+                const int k = lane + 32 * m;
+                const double v = (vd[j] && k < TC_KF_USED) ? vf[j][m] - centre[k] : 0.0;
+                const __half h = __double2half(v);
+                const __half l = __double2half((v - (double)__half2float(h)) * 2048.0);
+                *reinterpret_cast<__half *>(smem + kOffAhi + tc_sw128(TC_M, row, k)) = h;
+                *reinterpret_cast<__half *>(smem + kOffAlo + tc_sw128(TC_M, row, k)) = l;
+                ssum = fma(v, v, ssum);
+            }
+            if (lane < TC_KI_USED) {
+                const double v = vd[j] ? vi[j] - centre[TC_KF + lane] : 0.0;
+                *reinterpret_cast<__half *>(smem + kOffAI + tc_sw128(TC_M, row, lane)) = __double2half(v);  // small integers: exact
+                ssum = fma(v, v, ssum);
+            }
+            ssum = fma(vce[j], vce[j], fma(vcl[j], vcl[j], ssum));
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) ssum += __shfl_xor_sync(0xffffffffu, ssum, o);
+            const double f22 = __shfl_sync(0xffffffffu, vi[j], 0);   // extension_arm_length: zero only in the all-zero row of an invalid candidate
+            const double ce = __shfl_sync(0xffffffffu, vce[j], TC_KI_USED), cl = __shfl_sync(0xffffffffu, vcl[j], TC_KI_USED);
+            if (lane == 0) {
+                const bool finite = fabs(ssum) <= 1.7976931348623157e308;
+                rowState[row] = !vd[j] ? 0 : (f22 == 0.0 ? 1 : (finite ? 2 : 3));
+                rowR[row] = finite ? -gamma * ssum : 0.0;
+                rowCe[row] = finite ? 2.0 * gamma * ce : 0.0;
+                rowCl[row] = finite ? 2.0 * gamma * cl : 0.0;
+            }
         }
     }
     // generic-proxy writes of the operand -> visible to the tensor core (async proxy); TMEM address -> everyone
@@ -305,7 +310,7 @@ k_svr_tc(const DevRegion *__restrict__ regions, const int64_t *__restrict__ tile
         }
     } else if (warp >= kEpiWarp0) {
         // ======================= epilogue: thread = candidate row (TMEM lane), half of the 64 columns =======================
-        const int q = warp & 3, half = (warp - kEpiWarp0) >> 2, row = q * 32 + lane;
+        const int q = warp & 3, quarter = (warp - kEpiWarp0) >> 2, row = q * 32 + lane;   // quarter: which 16 of the 64 columns
         const double R = rowR[row], xce = rowCe[row], xcl = rowCl[row];
         const int state = rowState[row];
         const bool copies = xce != 0.0 || xcl != 0.0;
@@ -317,51 +322,46 @@ k_svr_tc(const DevRegion *__restrict__ regions, const int64_t *__restrict__ tile
             mbar_wait(&d_full[ds], (j >> 1) & 1);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             const uint8_t *stage = smem + kOffB + s * TC_STAGE_BYTES;
-            const double *sce = reinterpret_cast<const double *>(stage + 2 * TC_B_F_BYTES + TC_B_I_BYTES), *scl = sce + TC_N;
-            const double *wt = reinterpret_cast<const double *>(stage + TC_IMG_BYTES);
-            const uint32_t t0 = tmem_d + ((uint32_t)(q * 32) << 16) + (uint32_t)(ds * 3 * TC_N + half * 32);
+            const double *sce = reinterpret_cast<const double *>(stage + 2 * TC_B_F_BYTES + TC_B_I_BYTES) + quarter * 16, *scl = sce + TC_N;
+            const double *wt = reinterpret_cast<const double *>(stage + TC_IMG_BYTES) + quarter * 16;
+            const uint32_t t0 = tmem_d + ((uint32_t)(q * 32) << 16) + (uint32_t)(ds * 3 * TC_N + quarter * 16);
+            uint32_t vh[2][8], vx[2][8], vi[2][8];
 #pragma unroll
-            for (int c0 = 0; c0 < 32; c0 += 16) {
-                uint32_t vh[16], vx[16], vi[16];
-                tmem_ld16(t0 + c0, vh);
-                tmem_ld16(t0 + TC_N + c0, vx);
-                tmem_ld16(t0 + 2 * TC_N + c0, vi);
-                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-                if (c0 == 16) {
-                    // every TMEM read of this accumulator stage is done: hand it back to the MMA issuer
-                    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(&d_empty[ds]);
+            for (int c = 0; c < 2; c++) {
+                tmem_ld8(t0 + c * 8, vh[c]);
+                tmem_ld8(t0 + TC_N + c * 8, vx[c]);
+                tmem_ld8(t0 + 2 * TC_N + c * 8, vi[c]);
+            }
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+            // every TMEM read of this accumulator stage is done: hand it back to the MMA issuer
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&d_empty[ds]);
+#pragma unroll
+            for (int c = 0; c < 2; c++) {
+                double e[8];
+#pragma unroll
+                for (int i = 0; i < 8; i++) {
+                    const float f = fmaf(__uint_as_float(vx[c][i]), 1.0f / 2048.0f, __uint_as_float(vh[c][i]));
+                    const double d = (double)f + (double)__uint_as_float(vi[c][i]);
+                    e[i] = fma(d, g2, R);
                 }
+                if (copies) {
 #pragma unroll
-                for (int h8 = 0; h8 < 16; h8 += 8) {
-                    double e[8];
-#pragma unroll
-                    for (int i = 0; i < 8; i++) {
-                        const float f = fmaf(__uint_as_float(vx[h8 + i]), 1.0f / 2048.0f, __uint_as_float(vh[h8 + i]));
-                        const double d = (double)f + (double)__uint_as_float(vi[h8 + i]);
-                        e[i] = fma(d, g2, R);
-                    }
-                    if (copies) {
-#pragma unroll
-                        for (int i = 0; i < 8; i++) {
-                            const int col = half * 32 + c0 + h8 + i;
-                            e[i] = fma(xce, sce[col], fma(xcl, scl[col], e[i]));
-                        }
-                    }
-                    expn<8>(e, etab);
-#pragma unroll
-                    for (int i = 0; i < 8; i++) acc = fma(e[i], wt[half * 32 + c0 + h8 + i], acc);
+                    for (int i = 0; i < 8; i++) e[i] = fma(xce, sce[c * 8 + i], fma(xcl, scl[c * 8 + i], e[i]));
                 }
+                expn<8>(e, etab);
+#pragma unroll
+                for (int i = 0; i < 8; i++) acc = fma(e[i], wt[c * 8 + i], acc);
             }
             __syncwarp();
             if (lane == 0) mbar_arrive(&b_empty[s]);  // constants of the stage are consumed
         }
-        // the two column halves of a row
-        if (half == 1) part[row] = acc;
+        // the four column quarters of a row
+        if (quarter > 0) part[(quarter - 1) * TC_M + row] = acc;
         asm volatile("bar.sync 1, %0;" ::"n"(kEpiWarps * 32) : "memory");
-        if (half == 0 && row < n_rows) {
-            const double total = acc + part[row];
+        if (quarter == 0 && row < n_rows) {
+            const double total = ((acc + part[row]) + part[TC_M + row]) + part[2 * TC_M + row];
             const double nan = __longlong_as_double(0x7ff8000000000000LL);
             out[g0 + row] = state == 2 ? total - rho : (state == 3 ? -rho : (state == 1 ? zero_score : nan));
         }
@@ -488,7 +488,7 @@ int launch_svr_tc(mg_ctx *ctx, const mg_panel *p, const double *d_x, int64_t g0,
     CUDA_TRY(ctx, cudaMemcpyAsync(d_reg, reg.data(), reg.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
     mg_time_begin(ctx, TM_SVR, g1 - g0);
     k_svr_tc<<<(unsigned)tiles, kThreads, kSmemBytes, ctx->stream>>>(p->d_regions, d_off, d_reg, n_spans, d_x, g0, d_valid, ctx->d_tc_img, d_w,
-                                                                    ctx->d_tc_centre, ctx->d_exp2tab, ctx->n_sv_pad, ctx->gamma, ctx->rho,
+                                                                    ctx->d_tc_centre, ctx->d_exp2tab256, ctx->n_sv_pad, ctx->gamma, ctx->rho,
                                                                     ctx->zero_score, d_out);
     mg_time_end(ctx);
     CUDA_TRY(ctx, cudaGetLastError());

@@ -248,6 +248,10 @@ extern "C" int mg_create(int device, mg_ctx **out)
     for (int j = 0; j < 64; j++) e2tab[j] = exp2((double)j / 64.0);
     if ((e = cudaMalloc(&ctx->d_exp2tab, sizeof e2tab)) != cudaSuccess) return fail("cudaMalloc", e);
     cudaMemcpy(ctx->d_exp2tab, e2tab, sizeof e2tab, cudaMemcpyHostToDevice);
+    double e2tab256[256];
+    for (int j = 0; j < 256; j++) e2tab256[j] = exp2((double)j / 256.0);
+    if ((e = cudaMalloc(&ctx->d_exp2tab256, sizeof e2tab256)) != cudaSuccess) return fail("cudaMalloc", e);
+    cudaMemcpy(ctx->d_exp2tab256, e2tab256, sizeof e2tab256, cudaMemcpyHostToDevice);
     if ((e = cudaMalloc(&ctx->d_cfg, sizeof(DevConfig))) != cudaSuccess) return fail("cudaMalloc", e);
     if ((e = cudaMalloc(&ctx->d_work, 4 * sizeof(unsigned long long))) != cudaSuccess) return fail("cudaMalloc", e);
     cudaMemset(ctx->d_work, 0, 4 * sizeof(unsigned long long));
@@ -291,7 +295,7 @@ extern "C" void mg_destroy(mg_ctx *ctx)
     for (auto e : ctx->ev_free) cudaEventDestroy(e);
     if (ctx->sw_a) { cudaEventDestroy(ctx->sw_a); cudaEventDestroy(ctx->sw_b); }
     free_model(ctx);
-    cudaFree(ctx->d_x); cudaFree(ctx->d_fdesc); cudaFree(ctx->d_fdesc_win); cudaFree(ctx->d_logcopy); cudaFree(ctx->d_exp2tab); cudaFree(ctx->d_cfg); cudaFree(ctx->d_fact); cudaFree(ctx->d_work);
+    cudaFree(ctx->d_x); cudaFree(ctx->d_fdesc); cudaFree(ctx->d_fdesc_win); cudaFree(ctx->d_logcopy); cudaFree(ctx->d_exp2tab); cudaFree(ctx->d_exp2tab256); cudaFree(ctx->d_cfg); cudaFree(ctx->d_fact); cudaFree(ctx->d_work);
     cudaStreamDestroy(ctx->stream);
     delete ctx;
 }

@@ -138,7 +138,7 @@ __host__ __device__ inline uint32_t fd_pack(uint32_t kind, uint32_t part, uint32
 #define TC_KI 64           // integer columns, padded to one 128-byte operand row (19 used, 32 multiplied)
 #define TC_KI_USED 19
 #define TC_STAGES 3
-#define TC_THREADS 384
+#define TC_THREADS 640          // 4 service warps (producer, MMA issuer, TMEM allocator, spare) + 16 epilogue warps
 #define TC_A_F_BYTES (2 * TC_M * 128)      // two K blocks of 64 FP16 columns x 128 rows
 #define TC_A_I_BYTES (TC_M * 128)
 #define TC_B_F_BYTES (2 * TC_N * 128)
@@ -185,6 +185,7 @@ struct mg_ctx {
     uint32_t *d_fdesc_win = nullptr;  // [192] the same with prefix-table rows (window front-end)
     double *d_logcopy = nullptr;    // [102] log10(copy) for copy 0..100 (glibc), [101] = 2.0
     double *d_exp2tab = nullptr;    // [64] 2^(j/64), K-svr's exp table
+    double *d_exp2tab256 = nullptr; // [256] 2^(j/256), the tensor-core kernel's
     unsigned long long *d_work = nullptr;  // [0..2] DMMAs, exp elements, gathered triples EXECUTED by the factored K-svr since the
                                            // last mg_reset_timings (tasks that exit after the claim phase add nothing); [3] scratch
     // model
