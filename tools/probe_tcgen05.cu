@@ -125,6 +125,69 @@ __global__ void __launch_bounds__(128, 1) k_probe(const float *__restrict__ a_im
     if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "r"(N < 32 ? 32 : N) : "memory");
 }
 
+// ---- issue-rate probe: how long does one kind::f16 M128 x N x K16 MMA occupy the tensor pipe, per N? ----
+template <int N>
+__global__ void __launch_bounds__(128, 1) k_rate(long long *cycles, int iters)
+{
+    extern __shared__ __align__(1024) uint8_t smem[];
+    __shared__ __align__(8) uint64_t bar;
+    __shared__ uint32_t tmem_base_s;
+    const int tid = threadIdx.x, warp = tid >> 5;
+    for (int i = tid; i < (128 + 256) * 128 / 4; i += 128) reinterpret_cast<uint32_t *>(smem)[i] = 0x3c003c00u;  // FP16 ones
+    if (tid == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(&bar)), "r"(1) : "memory");
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)), "r"(512) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_d = tmem_base_s;
+    if (tid == 0) {
+        const uint32_t idesc = (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);  // F16 x F16 -> F32
+        const uint64_t da = make_desc(smem_u32(smem)), db = make_desc(smem_u32(smem + 128 * 128));
+        const long long t0 = clock64();
+        for (int i = 0; i < iters; i++) {
+            const uint32_t d = tmem_d + (uint32_t)((i & 1) * N);  // two accumulators, alternating
+            asm volatile(
+                "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(d),
+                "l"(da), "l"(db), "r"(idesc), "r"(i > 1 ? 1u : 0u)
+                : "memory");
+        }
+        asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&bar)) : "memory");
+        uint32_t done = 0;
+        while (!done)
+            asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}\n" : "=r"(done) : "r"(smem_u32(&bar)), "r"(0) : "memory");
+        cycles[blockIdx.x] = clock64() - t0;
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "r"(512) : "memory");
+}
+
+template <int N>
+static int run_rate()
+{
+    long long *d_c, h[148];
+    CHECK(cudaMalloc(&d_c, sizeof h));
+    const size_t smem = (128 + 256) * 128 + 1024;
+    CHECK(cudaFuncSetAttribute(k_rate<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int iters = 4096;
+    k_rate<N><<<148, 128, smem>>>(d_c, iters);
+    CHECK(cudaDeviceSynchronize());
+    CHECK(cudaMemcpy(h, d_c, sizeof h, cudaMemcpyDeviceToHost));
+    long long mx = 0;
+    for (int i = 0; i < 148; i++) mx = h[i] > mx ? h[i] : mx;
+    printf("M128 N%-3d K16 kind::f16: %.1f cycles per MMA on every SM at once (=> %.0f MAC/clk/SM)\n", N, (double)mx / iters, 128.0 * N * 16 / ((double)mx / iters));
+    cudaFree(d_c);
+    return 0;
+}
+
 static float tf32_round(float x)
 {
     uint32_t u;
@@ -181,6 +244,10 @@ int main()
     rc |= run_case<64, 32>();
     rc |= run_case<64, 128>();
     rc |= run_case<128, 64>();
+    run_rate<32>();
+    run_rate<64>();
+    run_rate<128>();
+    run_rate<256>();
     printf(rc ? "PROBE FAILED\n" : "PROBE PASSED\n");
     return rc;
 }
