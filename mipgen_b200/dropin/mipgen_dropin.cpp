@@ -18,17 +18,21 @@
 //   3. on a miss, scores in ONE device call every remaining scan start of the region for
 //      the whole pattern (a superset of what the score-dependent pruning will ask for,
 //      SURVEY.md F4), and answers the following ~1e5 calls from that grid;
-//   4. verifies each answer's geometry and sequences against the object before using it and
-//      re-scores the single candidate explicitly (mg_score_candidates) whenever anything
-//      differs -- e.g. arm copy numbers other than 1, which only the object knows
-//      (mipgen.cpp:612-613).
+//   4. takes the arm copy numbers of the region from the file mipgen's find_copy wrote just before
+//      (<project>.oligo_copy_count.sam, mipgen.cpp:558-596; project name from the process's own command
+//      line), since the caller's copy map is private (mipgen.cpp:83) and reaches the scoring classes only
+//      one object at a time (mipgen.cpp:612-613);
+//   5. verifies each answer's geometry, sequences and copy numbers against the object before using it
+//      and re-scores the single candidate explicitly (mg_score_candidates) whenever anything differs.
 #include <stdint.h>
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
+#include <fstream>
 #include <set>
+#include <unordered_map>
 
 #include "Featurev5.h"
 #include "SVMipv4.h"
@@ -70,6 +74,61 @@ static std::set<Featurev5 *> &registry()
 
 struct Combo { int capture, ext, lig; };
 
+// Arm copy numbers.  mipgen keeps them in a private map (copy_chr_start_stop, mipgen.cpp:83) and hands them to the scoring
+// classes one object at a time (mipgen.cpp:612-613).  A region batch needs them up front, so the shim reads the file the map
+// was filled from: find_copy (mipgen.cpp:558-596) has already written <project>.oligo_copy_count.sam when tile_regions starts;
+// the project name is taken from this process's own command line.  Every grid look-up is still checked against the copies
+// the object carries (same_sequences), so a missing or different file can only cost speed, never correctness.
+struct CopyMap {
+    bool tried = false, loaded = false;
+    std::unordered_map<std::string, std::unordered_map<uint64_t, int>> by_chr;
+    static uint64_t key(int start, int stop) { return ((uint64_t)(uint32_t)start << 32) | (uint32_t)stop; }
+
+    void load()
+    {
+        tried = true;
+        std::ifstream cl("/proc/self/cmdline", std::ios::binary);
+        std::string all((std::istreambuf_iterator<char>(cl)), std::istreambuf_iterator<char>()), project;
+        for (size_t at = 0; at < all.size();) {
+            const std::string arg(all.c_str() + at);
+            at += arg.size() + 1;
+            if (arg == "-project_name" && at < all.size()) project = std::string(all.c_str() + at);
+        }
+        if (project.empty()) return;
+        std::ifstream sam((project + ".oligo_copy_count.sam").c_str());
+        if (!sam) return;
+        std::string line;
+        while (std::getline(sam, line)) {
+            if (line.size() <= 1 || line[0] == '@') continue;
+            // the reference's own parse (mipgen.cpp:572-590): "chr<chr>:<start>-<stop>\t...", copy = X0:i:<n>, 100 without the tag
+            const size_t c0 = line.find("chr", 0);
+            if (c0 == std::string::npos) continue;
+            const size_t c1 = line.find(':', c0 + 3), d = line.find('-', c1 + 1), t = line.find('\t', d + 1);
+            if (c1 == std::string::npos || d == std::string::npos || t == std::string::npos) continue;
+            const int start = atoi(line.substr(c1 + 1, d - c1 - 1).c_str()), stop = atoi(line.substr(d + 1, t - d - 1).c_str());
+            const size_t x0 = line.find("X0:i:", 0);
+            by_chr[line.substr(c0 + 3, c1 - c0 - 3)][key(start, stop)] = x0 != std::string::npos ? atoi(line.c_str() + x0 + 5) : 100;
+        }
+        loaded = true;
+    }
+
+    // copy_chr_start_stop[chr][start][stop]; an absent key reads as 0 there (operator[])
+    int get(const std::string &chr, int start, int stop) const
+    {
+        auto c = by_chr.find(chr);
+        if (c == by_chr.end()) return 0;
+        auto it = c->second.find(key(start, stop));
+        return it == c->second.end() ? 0 : it->second;
+    }
+};
+
+static CopyMap &copy_map()
+{
+    static CopyMap m;
+    if (!m.tried) m.load();
+    return m;
+}
+
 // One device batch: scan starts [s0, s1] x the first n_pairs/n_caps of the pattern.
 struct Batch {
     const Featurev5 *feature = nullptr;
@@ -80,6 +139,7 @@ struct Batch {
     bool has_logistic = false, has_svr = false;
     std::vector<uint8_t> valid;
     std::vector<double> logistic, svr, feats;
+    std::vector<int> oligo_sizes, copies;  // [n_oligo][seq_len] arm copy table the batch was scored with; empty => every copy 1
     int seq_start = 0;
     std::string seq;  // copy of the region sequence the batch was computed from
     double lrc[MG_NLRC];
@@ -93,6 +153,18 @@ struct Batch {
         if (p < 0) return -1;
         int ci = (max_cap - capture) / inc;
         return ((((long)(s - s0)) * n_cap + ci) * (long)ext.size() + p) * 2 + strand;
+    }
+
+    // the copy number the batch assumed for the arm [start, start + len)
+    int copy_of(int start, int len) const
+    {
+        if (copies.empty()) return 1;
+        for (size_t k = 0; k < oligo_sizes.size(); k++)
+            if (oligo_sizes[k] == len) {
+                const int i = start - seq_start;
+                return (i < 0 || i >= (int)seq.size()) ? 0 : copies[k * seq.size() + (size_t)i];
+            }
+        return 0;
     }
 };
 
@@ -152,7 +224,10 @@ static const Featurev5 *find_feature(const SVMipv4 *m)
 // here: the sequences the object carries are the ones the batch was computed from.)
 static bool same_sequences(const Batch &b, const SVMipv4 *m)
 {
-    if (m->ext_probe_copy != 1 || m->lig_probe_copy != 1) return false;  // grid assumes copy 1/1
+    // the copies the object carries are the ones the grid point was scored with
+    if (m->ext_probe_copy != b.copy_of(m->ext_probe_start, m->extension_arm_length) ||
+        m->lig_probe_copy != b.copy_of(m->lig_probe_start, m->ligation_arm_length))
+        return false;
     if ((int)m->ext_probe_sequence.size() != m->extension_arm_length || (int)m->lig_probe_sequence.size() != m->ligation_arm_length ||
         (int)m->scan_target_sequence.size() != m->scan_size)
         return false;
@@ -207,11 +282,30 @@ static void run_batch(const Featurev5 *f, int s0, int s1, bool want_svr, const d
     cfg.n_pairs = (int)b.ext.size();
     cfg.ext_len = b.ext.data();
     cfg.lig_len = b.lig.data();
+    std::vector<int> sizes;  // oligo sizes of this pattern (the copy table below is built for them)
+    if (copy_map().loaded) {
+        for (auto &p : pairs) { sizes.push_back(p.first); sizes.push_back(p.second); }
+        std::sort(sizes.begin(), sizes.end());
+        sizes.erase(std::unique(sizes.begin(), sizes.end()), sizes.end());
+        cfg.n_oligo_sizes = (int)sizes.size();
+        cfg.oligo_sizes = sizes.data();
+    }
     if (mg_set_config(ctx(), &cfg) != MG_OK) fatal("mg_set_config", ctx());
 
     b.seq = f->chromosomal_sequence;
     b.seq_start = f->chromosomal_sequence_start_position;
     memcpy(b.lrc, lrc ? lrc : f->long_range_content, sizeof b.lrc);
+    // arm copy table of this region from the file find_copy wrote, for every arm length of the pattern
+    const CopyMap &cm = copy_map();
+    if (cm.loaded) {
+        for (auto &p : pairs) { b.oligo_sizes.push_back(p.first); b.oligo_sizes.push_back(p.second); }
+        std::sort(b.oligo_sizes.begin(), b.oligo_sizes.end());
+        b.oligo_sizes.erase(std::unique(b.oligo_sizes.begin(), b.oligo_sizes.end()), b.oligo_sizes.end());
+        b.copies.assign(b.oligo_sizes.size() * b.seq.size(), 0);
+        for (size_t k = 0; k < b.oligo_sizes.size(); k++)
+            for (size_t i = 0; i < b.seq.size(); i++)
+                b.copies[k * b.seq.size() + i] = cm.get(f->chr, b.seq_start + (int)i, b.seq_start + (int)i + b.oligo_sizes[k] - 1);
+    }
     mg_region r;
     memset(&r, 0, sizeof r);
     r.seq = b.seq.data();
@@ -223,6 +317,7 @@ static void run_batch(const Featurev5 *f, int s0, int s1, bool want_svr, const d
     r.scan_begin = s0;  // explicit scan range: the rest of the region from the caller's position
     r.scan_end = s1;
     r.lrc = b.lrc;
+    r.copies = b.copies.empty() ? nullptr : b.copies.data();
     int64_t n = mg_grid_size(ctx(), &r);
     b.valid.resize((size_t)n);
     b.logistic.resize((size_t)n);
@@ -264,7 +359,8 @@ static long locate(const SVMipv4 *m, bool need_svr, const double *lrc)
     Engine &e = engine();
     static bool hooked = false;
     if (!hooked) { atexit(report_at_exit); hooked = true; }
-    if (m->ext_probe_copy != 1 || m->lig_probe_copy != 1) return -1;
+    // without the copy file the grids assume copy 1 for every arm: anything else goes the explicit way
+    if (!copy_map().loaded && (m->ext_probe_copy != 1 || m->lig_probe_copy != 1)) return -1;
     if (m->strand != "+" && m->strand != "-") return -1;
     const int strand = m->strand == "-";
     const int capture = m->scan_size + m->extension_arm_length + m->ligation_arm_length;

@@ -54,13 +54,14 @@ def workspace(oracle):
     return dict(dir=d, gdir=gdir, bed=bed, model=model)
 
 
-def run_cli(binary, ws, name, extra):
+def run_cli(binary, ws, name, extra, env_extra=None):
     run = os.path.join(ws["dir"], name)
     os.makedirs(run)
     exe = os.path.join(run, "mipgen")
     os.symlink(binary, exe)                      # argv[0]'s directory is where the model is looked up
     shutil.copy(ws["model"], os.path.join(run, "mipgen_svr.model"))
     env = dict(os.environ, PATH=STUB_DIR + os.pathsep + os.environ.get("PATH", ""), MIPGEN_B200_VERBOSE="1")
+    env.update(env_extra or {})
     cmd = [exe, "-regions_to_scan", ws["bed"], "-project_name", "p", "-bwa_genome_index", os.path.join(ws["gdir"], "chr1.fa"),
            "-genome_dir", ws["gdir"]] + extra
     r = subprocess.run(cmd, cwd=run, env=env, capture_output=True, text=True, timeout=900)
@@ -78,6 +79,26 @@ CASES = {
     "mixed": ["-min_capture_size", "157", "-max_capture_size", "162", "-score_method", "mixed", "-arm_length_sums", "41,45",
               "-tag_sizes", "4,4"],
 }
+
+
+@needs_binaries
+@pytest.mark.parametrize("mode", ["logistic", "svr"])
+def test_dropin_cli_with_arm_copy_numbers_other_than_one(workspace, mode):
+    """A bwa that reports extra copies for some arms (oracle/stub_bwa.sh, MIPGEN_STUB_RULES=2): the shim takes the region's copy
+    table from the <project>.oligo_copy_count.sam find_copy wrote (mipgen.cpp:558-596), so candidates with copies != 1 are served
+    from the device grid too instead of one launch per candidate; files stay byte-identical."""
+    flags = CASES["logistic"] if mode == "logistic" else CASES["svr"]
+    env = {"MIPGEN_STUB_RULES": "2"}
+    ref_dir, _ = run_cli(REF_CLI, workspace, "ref_copies_" + mode, flags, env)
+    new_dir, log = run_cli(DROPIN_CLI, workspace, "b200_copies_" + mode, flags, env)
+    for f in OUTPUTS:
+        assert filecmp.cmp(os.path.join(ref_dir, "p." + f), os.path.join(new_dir, "p." + f), shallow=False), "%s differs" % f
+    copies = [l.split("\t")[5] for l in open(os.path.join(ref_dir, "p.all_mips.txt")) if not l.startswith(">")]
+    assert sum(c != "1" for c in copies) > 100, "the stub must have produced arm copies other than 1"
+    line = [l for l in log.splitlines() if "device batches" in l][-1]
+    explicit = int(line.split("explicit candidates")[1].split(",")[0])
+    lookups = int(line.rsplit(" ", 1)[1])
+    assert explicit == 0 and lookups > 1000, line
 
 
 @needs_binaries

@@ -208,3 +208,150 @@ def test_score_only_harness_cfg1():
         assert rel_err([sv[k]], [oracle.svm_predict(h, wf)]) <= 1e-9
     oracle.svm_free(h)
     ctx.close()
+
+
+# ----------------------------------------------------------------------------------------------------------
+# whole bench panel against the oracle: every candidate, not a sample
+# ----------------------------------------------------------------------------------------------------------
+def _oracle_region_job(args):
+    """One region through the oracle in a forked worker: returns (valid, logistic, sha256 of the feature rows)."""
+    import hashlib
+    from oracle_api import Oracle
+    r, cfg = args
+    o = Oracle()
+    v, lo, _s, ft = o.grid_region(r, cfg, None, want_logistic=True, want_feats=True)
+    ft[~v.astype(bool)] = 0.0
+    return v, lo, hashlib.sha256(np.ascontiguousarray(ft).tobytes()).hexdigest()
+
+
+def test_whole_bench_panel_features_and_logistic_equal_the_oracle(setup):
+    """All 2.53 M candidates of the bench panel: validity and the 192 features bit-exact (compared per region through a digest of
+    the raw feature bytes), logistic <= 1e-12 relative -- the oracle runs on the host cores, one region per task."""
+    import hashlib
+    import multiprocessing as mp
+    ctx, cfg, regions, offs = setup["ctx"], setup["cfg"], setup["regions"], setup["offs"]
+    with mp.get_context("fork").Pool(min(16, os.cpu_count() or 1)) as pool:
+        want = pool.map(_oracle_region_job, [(r, cfg) for r in regions], chunksize=1)
+    worst = 0.0
+    for i0 in range(0, len(regions), 6):   # feature rows of six regions at a time (~0.4 GB on the host)
+        part = regions[i0:i0 + 6]
+        o2, v2, _l, _s, ft = ctx.score_regions(part, mg.MG_WANT_FEATURES)
+        for k, r in enumerate(part):
+            i = i0 + k
+            a, b = int(offs[i]), int(offs[i + 1])
+            wv, wl, wdigest = want[i]
+            assert np.array_equal(setup["valid"][a:b], wv) and np.array_equal(v2[o2[k]:o2[k + 1]], wv), "validity differs in region %d" % i
+            rows = ft[o2[k]:o2[k + 1]].copy()
+            rows[~wv.astype(bool)] = 0.0
+            assert hashlib.sha256(np.ascontiguousarray(rows).tobytes()).hexdigest() == wdigest, "feature rows differ in region %d" % i
+            ok = wv.astype(bool)
+            worst = max(worst, rel_err(setup["lo"][a:b][ok], wl[ok]))
+    print("whole panel: %d candidates, features bit-exact, logistic max rel err %.2e" % (int(offs[-1]), worst))
+    assert worst <= 1e-12
+
+
+def _oracle_svr_job(args):
+    from oracle_api import Oracle
+    model, rows = args
+    o = Oracle()
+    h = o.svm_load_model(model)
+    out = o.svm_predict_rows(h, rows)
+    o.svm_free(h)
+    return out
+
+
+def test_stratified_svr_sample_of_the_bench_panel_equals_the_oracle(setup):
+    """12,000 candidates of the bench panel, 200 per region (so every region, both strands and all arm pairs are hit), through
+    libsvm's arithmetic (2048 SV): the factored FP64 kernel <= 1e-9, the tensor-core form <= 1e-7 (north star: 1e-6)."""
+    import multiprocessing as mp
+    ctx, regions, offs, valid = setup["ctx"], setup["regions"], setup["offs"], setup["valid"]
+    rng = np.random.default_rng(2024)
+    picks = np.concatenate([np.sort(rng.choice(np.nonzero(valid[offs[i]:offs[i + 1]])[0], 200, replace=False)) + offs[i] for i in range(len(regions))])
+    rows = []
+    for i0 in range(0, len(regions), 6):
+        part = regions[i0:i0 + 6]
+        o2, _v, _l, _s, ft = ctx.score_regions(part, mg.MG_WANT_FEATURES)
+        for k in range(len(part)):
+            sel = picks[(picks >= offs[i0 + k]) & (picks < offs[i0 + k + 1])] - offs[i0 + k]
+            rows.append(ft[o2[k] + sel])
+    rows = np.concatenate(rows)
+    n_proc = min(16, os.cpu_count() or 1)
+    with mp.get_context("fork").Pool(n_proc) as pool:
+        want = np.concatenate(pool.map(_oracle_svr_job, [(setup["model"], c) for c in np.array_split(rows, n_proc)]))
+    e64 = rel_err(setup["sv"][picks], want)
+    ctx.set_svr_mode(3)
+    _o, _v, _l, tc, _f = ctx.score_regions(regions, mg.MG_WANT_SVR)
+    ctx.set_svr_mode(0)
+    etc = rel_err(tc[picks], want)
+    print("SVR vs libsvm arithmetic on %d stratified candidates: FP64 factored kernel %.2e, tensor-core kernel %.2e" % (picks.size, e64, etc))
+    assert e64 <= 1e-9 and etc <= 1e-7
+
+
+def test_gpu_equals_the_compiled_reference_directly(setup):
+    """The same comparison against the unmodified reference objects themselves (oracle/_ref/libmipgen_ref.so: SVMipv4::get_parameters,
+    get_score, svm_predict), not their restatement: one region of the bench panel, every candidate."""
+    from oracle_api import Ref, have_ref
+    if not have_ref():
+        pytest.skip("oracle/_ref not built (needs /root/reference at build time)")
+    ref = Ref()
+    ctx, cfg, regions, offs = setup["ctx"], setup["cfg"], setup["regions"], setup["offs"]
+    i = int(np.argmin(np.diff(offs)))   # the smallest region keeps the reference's 2048-SV predictions to a few seconds on one core
+    r = regions[i]
+    h = ref.svm_load_model(setup["model"])
+    wv, wl, ws, wf = ref.grid_region(r, cfg, h, want_logistic=True, want_svr=False, want_feats=True)
+    n = 40 * cfg.n_pairs * 2   # the first 40 scan starts = 4,560 candidates through the reference's svm_predict
+    want_svr = ref.svm_predict_rows(h, wf[:n])
+    ref.svm_free(h)
+    a = int(offs[i])
+    _o, v, lo, sv, ft = ctx.score_regions([r], mg.MG_WANT_LOGISTIC | mg.MG_WANT_SVR | mg.MG_WANT_FEATURES)
+    ok = wv.astype(bool)
+    assert np.array_equal(v, wv) and np.array_equal(ft[ok], wf[ok])
+    assert rel_err(lo[ok], wl[ok]) <= 1e-12
+    assert rel_err(sv[:n][ok[:n]], want_svr[ok[:n]]) <= 1e-9
+    assert np.array_equal(lo, setup["lo"][a:a + lo.size], equal_nan=True)
+    lrc_ref = ref.long_range_content(r.flank_seq, r.seq_start, r.seq_stop)
+    assert np.array_equal(lrc_ref, r.lrc), "K-lrc equals Featurev5::get_long_range_content bit for bit"
+
+
+def test_cfg5_shape_streams_through_bounded_memory():
+    """BASELINE configs[4] shape at 1/100 scale: 2,000 regions of U[100,200] bp, capture 162, SVR, through mg_tile_regions with a
+    small sub-batch bound (so the region list is walked in ~60 panels): winners equal the ones of plain per-region panels on a
+    sample, and an oracle sample of the winners' scores holds."""
+    from oracle_api import Oracle
+    from helpers import calibrated_model, small_config
+    oracle = Oracle()
+    cfg = panel.Config()
+    n = 2000
+    genome = panel.lcg_genome(panel.genome_length_for(n, 200, cfg, gap=300), 515)
+    regions = panel.make_regions(genome, n, 100, 200, cfg, 516, gap=300)
+    ctx = mg.Context(0)
+    ctx.set_config(cfg)
+    for r in regions[:5]:
+        r.lrc = ctx.long_range_content(r.flank_seq, r.seq_start, r.seq_stop)
+    for k, r in enumerate(regions[5:]):
+        r.lrc = regions[k % 5].lrc
+    _v, _l, _s, feats = oracle.grid_region(regions[0], cfg, None, want_logistic=False, want_feats=True)
+    model = calibrated_model(oracle, small_config((40, 45)), 96, 5, os.path.join(tmpdir(), "m.model"), feats[np.isfinite(feats[:, 0])][::97])
+    ctx.load_svr_model(model)
+    sel = dict(method=1, lower=1.5, upper=2.2)
+    t = mg.tile_regions(ctx, regions, mg.MG_WANT_SVR, select=sel, max_batch_candidates=1 << 20)
+    assert int(t.grid_off[-1]) > 5.5e7 and (t.scan_best >= 0).mean() > 0.99
+    h = oracle.svm_load_model(model)
+    for i in (0, 777, 1999):
+        r = regions[i]
+        pnl = ctx.panel([r])
+        pnl.score(mg.MG_WANT_SVR)
+        valid, _lo, sv, _ = pnl.fetch(valid=True, svr=True)
+        _so, sb, _po, pb = pnl.select([r], 1, 1.5, 2.2)
+        pnl.close()
+        assert np.array_equal(t.scan_best[t.scan_off[i]:t.scan_off[i + 1]], sb) and np.array_equal(t.pos_best[t.pos_off[i]:t.pos_off[i + 1]], pb)
+        has = sb >= 0
+        assert np.array_equal(t.scan_best_svr[t.scan_off[i]:t.scan_off[i + 1]][has], sv[sb[has]])
+        # the oracle on this region: same winners, scores within tolerance
+        wv, _wl, ws, _wf = oracle.grid_region(r, cfg, h, want_logistic=False, want_svr=True)
+        assert np.array_equal(valid, wv) and rel_err(sv, ws) <= 1e-9
+        enum_idx = oracle.tile_replay(r, cfg, wv, sv, 1, True, 2.2)
+        wsb, wpb = oracle.select(r, cfg, sv, enum_idx, 1.5, 2.2)
+        assert np.array_equal(sb, wsb) and np.array_equal(pb, wpb)
+    oracle.svm_free(h)
+    ctx.close()
