@@ -260,6 +260,24 @@ int64_t mg_format_mip_records(const mg_config *cfg, const mg_region *r, const in
                               const char *chr, const char *label, int feature_start, int feature_stop,
                               const char *universal_middle, int first_index, char *buf, int64_t cap);
 
+/* ---- the same records written on the device -------------------------------------------------------------
+ * n records of a scored panel, given by panel-global grid indices, numbered first_index, first_index + 1, ...; byte-identical to
+ * what mg_format_mip_records / print_details (mipgen.cpp:765-794) produce, incl. the score as `ostream << double` prints it (%g,
+ * correctly rounded from the exact binary value).  which: 0 = logistic scores, 1 = SVR scores.  meta[i] describes region i of the
+ * panel.  Returns the bytes written into buf (host memory, capacity cap), or a negative status: regions that carry TRF / SNP /
+ * mappability inputs are refused (their flags need design_mip). */
+typedef struct {
+    const char *chr;     /* Featurev5::chr   */
+    const char *label;   /* Featurev5::label */
+    int feature_start;   /* Featurev5::start_position (printed minus 1) */
+    int feature_stop;    /* Featurev5::stop_position  */
+} mg_record_meta;
+int64_t mg_panel_format_records(mg_ctx *ctx, mg_panel *p, const mg_record_meta *meta, const int64_t *idx, int64_t n, int which,
+                                const char *universal_middle, int first_index, char *buf, int64_t cap);
+/* printf("%g") of n doubles on the device, 32 bytes per value in out32 (not NUL-terminated), lengths in len (-1: magnitude outside
+ * [1e-12, 1e15), which the record formatter leaves to the host).  Exposed for tests. */
+int mg_format_g(mg_ctx *ctx, const double *values, int64_t n, char *out32, int *len);
+
 /* ---- one call per batch of Featurev5 objects: what tile_regions does per feature up to collapse_mips ----------
  * (mipgen.cpp:412-505: the candidate loop nest, condense_mips, collapse_mips), for a caller that keeps pick_mips
  * (mipgen.cpp:1506-1614) on the host.  Regions are walked in sub-batches of at most max_batch_candidates grid

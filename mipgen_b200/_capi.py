@@ -49,6 +49,10 @@ class MgSelectParams(C.Structure):
                 ("masked_arm_threshold", C.c_double)]
 
 
+class MgRecordMeta(C.Structure):
+    _fields_ = [("chr", C.c_char_p), ("label", C.c_char_p), ("feature_start", C.c_int), ("feature_stop", C.c_int)]
+
+
 class MgTileResult(C.Structure):
     _fields_ = [("scan_best", c_int64_p), ("pos_best", c_int64_p), ("scan_best_logistic", c_double_p),
                 ("scan_best_svr", c_double_p), ("valid", c_ubyte_p), ("logistic", c_double_p), ("svr", c_double_p)]
@@ -121,6 +125,9 @@ SYMBOLS = [
                                          c_ubyte_p, c_double_p, c_double_p]),
     ("mg_partition_regions", C.c_int, [C.POINTER(MgConfig), C.POINTER(MgRegion), C.c_int, C.c_int, c_int_p]),
     ("mg_panel_gather", C.c_int, [C.c_void_p, C.c_void_p, c_int64_p, C.c_int64, c_double_p, c_double_p]),
+    ("mg_panel_format_records", C.c_int64, [C.c_void_p, C.c_void_p, C.POINTER(MgRecordMeta), c_int64_p, C.c_int64, C.c_int, C.c_char_p,
+                                            C.c_int, C.c_void_p, C.c_int64]),
+    ("mg_format_g", C.c_int, [C.c_void_p, c_double_p, C.c_int64, C.c_void_p, c_int_p]),
 ]
 
 _lib = None
@@ -347,6 +354,27 @@ class Panel:
                                                      _ptr(sv, c_double_p)))
         return lo, sv
 
+    def format_records(self, regions: Sequence[Region], idx: np.ndarray, which: int, chrom: str = "1", first_index: int = 1,
+                       middle: Optional[str] = None, out: Optional[np.ndarray] = None):
+        """all_mips.txt / collapsed_mips.txt lines of the given panel-global grid indices, written on the device
+        (mg_panel_format_records).  Returns a uint8 array view of the bytes."""
+        idx = np.ascontiguousarray(idx, np.int64).reshape(-1)
+        meta = (MgRecordMeta * max(1, len(regions)))()
+        keep = []
+        for i, r in enumerate(regions):
+            lab = r.label.encode()
+            keep.append(lab)
+            meta[i] = MgRecordMeta(chrom.encode(), lab, r.start_flanked, r.stop_flanked)
+        mid = (middle if middle is not None else universal_middle()).encode()
+        cap = max(1, idx.size) * (512 + 3 * self.ctx.cfg.max_capture + len(mid) + 2 * len(chrom) + 32)
+        if out is None or out.size < cap:
+            out = np.empty(cap, np.uint8)
+        n = self.ctx.lib.mg_panel_format_records(self.ctx.h, self.h, meta, _ptr(idx, c_int64_p), idx.size, which, mid, first_index,
+                                                 out.ctypes.data_as(C.c_void_p), out.size)
+        if n < 0:
+            raise MgError("mg_panel_format_records failed (%d): %s" % (n, self.ctx.lib.mg_last_error(self.ctx.h).decode()))
+        return out[:n]
+
     def select(self, regions: Sequence[Region], method: int, lower: float, upper: float, heuristic: bool = True,
                max_arm_copy: int = 75, target_arm_copy: int = 20, masked_arm_threshold: float = 0.5):
         """condense_mips + collapse_mips on the device.  Returns (scan_offsets, scan_best[n,2], pos_offsets,
@@ -425,6 +453,14 @@ class Context:
 
     def svr_factored_available(self) -> int:
         return int(self.lib.mg_svr_factored_available(self.h))
+
+    def format_g(self, values: np.ndarray):
+        """printf('%g') of each value on the device (mg_format_g); returns a list of str (None where the device declines)."""
+        v = np.ascontiguousarray(values, np.float64).reshape(-1)
+        out = np.zeros((v.size, 32), np.uint8)
+        ln = np.zeros(v.size, np.int32)
+        self._check(self.lib.mg_format_g(self.h, _ptr(v, c_double_p), v.size, out.ctypes.data_as(C.c_void_p), _ptr(ln, c_int_p)))
+        return [bytes(out[i, :ln[i]]).decode() if ln[i] >= 0 else None for i in range(v.size)]
 
     def svr_tensor_core_available(self) -> bool:
         return bool(self.lib.mg_svr_tensor_core_available(self.h))

@@ -39,6 +39,6 @@ struct mipgen_b200_batch {
     std::vector<double> sb_logistic, sb_svr, logistic, svr;
     std::vector<uint8_t> valid;
     long n_batches = 0, n_objects = 0;
-    double device_seconds = 0;
+    double device_seconds = 0, setup_seconds = 0, prep_seconds = 0, objects_seconds = 0, records_seconds = 0;  // MIPGEN_B200_VERBOSE report
 };
 #endif

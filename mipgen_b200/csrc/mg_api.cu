@@ -845,7 +845,7 @@ extern "C" void mg_panel_destroy(mg_panel *p)
     mg_ctx *c = p->ctx;
     mg_dev_free(c, p->d_ftasks); mg_dev_free(c, p->d_w); mg_dev_free(c, p->d_w_tc);
     mg_dev_free(c, p->d_regions); mg_dev_free(c, p->d_tasks); mg_dev_free(c, p->d_codes); mg_dev_free(c, p->d_lrc); mg_dev_free(c, p->d_copies);
-    mg_dev_free(c, p->d_maskpf); mg_dev_free(c, p->d_snppf); mg_dev_free(c, p->d_unmap);
+    mg_dev_free(c, p->d_maskpf); mg_dev_free(c, p->d_snppf); mg_dev_free(c, p->d_unmap); mg_dev_free(c, p->d_ascii);
     mg_dev_free(c, p->d_valid); mg_dev_free(c, p->d_logistic); mg_dev_free(c, p->d_svr); mg_dev_free(c, p->d_feat);
     delete p;
 }
@@ -969,7 +969,7 @@ extern "C" int mg_panel_create(mg_ctx *ctx, const mg_region *regions, int n, mg_
             }
             if (r.unmappable) memcpy(&um[(size_t)p->h_regions[i].unmap_off], r.unmappable, (size_t)ctx->cfg.n_cap * r.seq_len);
         }
-        char *d_ascii = nullptr;
+        char *&d_ascii = p->d_ascii;  // kept: K-fmt-write prints the sequences
         P_TRY(mg_dev_alloc(ctx, (void **)&d_ascii, (size_t)codes));
         P_TRY(mg_dev_alloc(ctx, (void **)&p->d_codes, (size_t)codes));
         P_TRY(mg_dev_alloc(ctx, (void **)&p->d_regions, (size_t)n * sizeof(DevRegion)));
@@ -1003,7 +1003,6 @@ extern "C" int mg_panel_create(mg_ctx *ctx, const mg_region *regions, int n, mg_
         }
         int rc = launch_encode(ctx, d_ascii, p->d_codes, codes);
         cudaStreamSynchronize(ctx->stream);  // host staging vectors go out of scope
-        mg_dev_free(ctx, d_ascii);
         if (rc != MG_OK) { mg_panel_destroy(p); return rc; }
     }
     if (p->n_cand > 0) P_TRY(mg_dev_alloc(ctx, (void **)&p->d_valid, (size_t)p->n_cand));

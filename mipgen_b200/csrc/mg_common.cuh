@@ -248,6 +248,7 @@ struct mg_panel {
     int w_tc_n_sv_pad = 0;
     int span_cap = 0, pf_stride = 0;
     uint8_t *d_codes = nullptr;
+    char *d_ascii = nullptr;       // the sequences as given (the record formatter prints them)
     int64_t n_codes = 0;
     double *d_lrc = nullptr;       // [n_regions][44]
     int *d_copies = nullptr;

@@ -3,7 +3,7 @@
 (mipgen_b200/dropin/_build/mipgen: the same mipgen.cpp against the GPU library) and the batched caller
 (INTEGRATION.md route B: mg_panel_score + mg_panel_select + mg_format_mip_records, which writes collapsed_mips.txt
 itself) on one synthetic panel.  Outputs must be byte-identical; prints the timings as JSON.
-    python tools/cli_compare.py [n_regions] [n_sv]
+    python tools/cli_compare.py [n_regions] [n_sv] [svr_regions]
 """
 import filecmp
 import json
@@ -25,6 +25,7 @@ from helpers import calibrated_model, small_config  # noqa: E402
 
 REF = os.path.join(ROOT, "oracle", "_ref", "mipgen")
 NEW = os.path.join(ROOT, "mipgen_b200", "dropin", "_build", "mipgen")
+BATCHED = os.path.join(ROOT, "mipgen_b200", "dropin", "_build", "mipgen_batched")   # route C: loop nest + condense + collapse on the GPU
 STUB = os.path.join(ROOT, "oracle", "_ref")
 
 
@@ -116,7 +117,8 @@ def main():
     model = calibrated_model(oracle, small_config((40, 45)), n_sv, 3, os.path.join(d, "mipgen_svr.model"), sample)
     n_cand = sum(cfg.grid_size(r) for r in regions)
     out = {"regions": n_regions, "candidates": n_cand, "n_sv": n_sv}
-    for mode, nreg in (("logistic", n_regions), ("svr", max(2, n_regions // 10))):
+    svr_regions = int(sys.argv[3]) if len(sys.argv) > 3 else max(2, n_regions // 10)
+    for mode, nreg in (("logistic", n_regions), ("svr", svr_regions)):
         bed_m = bed
         if nreg != n_regions:
             bed_m = os.path.join(d, "t_%s.bed" % mode)
@@ -132,6 +134,17 @@ def main():
         bt = batched(cfg, regions[:nreg], mode, model, f_all, f_col)
         same_b = (filecmp.cmp(os.path.join(c, "p.collapsed_mips.txt"), f_col, shallow=False) and
                   filecmp.cmp(os.path.join(c, "p.all_mips.txt"), f_all, shallow=False))
+        # route C: the batched driver (reference mipgen.cpp patched at build time), same flags, silent and not
+        e, te, elog = run(BATCHED, d, "batched_" + mode, bed_m, gdir, model, extra)
+        same_c = all(filecmp.cmp(os.path.join(a, "p." + f), os.path.join(e, "p." + f), shallow=False)
+                     for f in ("picked_mips.txt", "collapsed_mips.txt", "snp_mips.txt"))
+        e2, te2, _ = run(BATCHED, d, "batched_full_" + mode, bed_m, gdir, model, extra, silent=False)
+        same_c2 = all(filecmp.cmp(os.path.join(c, "p." + f), os.path.join(e2, "p." + f), shallow=False)
+                      for f in ("picked_mips.txt", "collapsed_mips.txt", "snp_mips.txt", "all_mips.txt"))
+        out[mode + "_batched_cli"] = {"regions": nreg, "reference_silent_s": round(ta, 2), "batched_silent_s": round(te, 2),
+                                      "speedup_silent": round(ta / te, 1), "identical_picked_collapsed_snp": same_c,
+                                      "reference_not_silent_s": round(tc, 2), "batched_not_silent_s": round(te2, 2),
+                                      "speedup_not_silent": round(tc / te2, 1), "identical_all_files_not_silent": same_c2}
         out[mode] = {"regions": nreg, "candidates": sum(cfg.grid_size(r) for r in regions[:nreg]), "reference_s": round(ta, 2),
                      "dropin_s": round(tb, 2), "identical_outputs": same, "shim": log[-1] if log else "",
                      "reference_not_silent_s": round(tc, 2), "batched_caller": bt,
