@@ -322,10 +322,13 @@ def main():
     os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
     import torch
     import mipgen_b200 as mg
+    cpu_group = None
     if world > 1:
         import torch.distributed as dist
         torch.cuda.set_device(local_rank)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        # host-side waiting for the phases one rank runs alone (an NCCL barrier would spin ON the other GPUs meanwhile)
+        cpu_group = dist.new_group(backend="gloo")
     ctx = mg.Context(local_rank)
     ctx.set_config(cfg)
     model_path = build_model(ctx, cfg, work)
@@ -436,14 +439,20 @@ def main():
     barrier()
     pnl.close()
 
+    def host_barrier():
+        ctx.sync()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier(group=cpu_group)
+
     extras = None
     if not args.no_extras and rank == 0:
         extras = extra_blocks(ctx, cfg, work, args)
-    barrier()
+    host_barrier()
     target = None
     if not args.no_target:
         target = target_block(args, rank, world, work, barrier)
-    barrier()
+    host_barrier()
 
     if rank == 0:
         peak, peak_src = fp64_peak_tflops()

@@ -154,6 +154,14 @@ __device__ __forceinline__ void expn(double (&t)[N], uint32_t tab256)
 #define MG_TC_ABLATE 0
 #endif
 
+// -DMG_TC_TRACE: CTA 1000 of a launch writes clock64 timestamps of its pipeline events to a global buffer (tools/trace_tc.py)
+#ifdef MG_TC_TRACE
+__device__ long long g_tc_trace[64 * 8];
+#define TC_STAMP(j, k) do { if (blockIdx.x == 1000) g_tc_trace[(j) * 8 + (k)] = clock64(); } while (0)
+#else
+#define TC_STAMP(j, k) do { } while (0)
+#endif
+
 constexpr int kThreads = TC_THREADS;
 constexpr int kEpiWarp0 = 0, kEpiWarps = 16;   // warps 16..19: producer, MMA issuer, TMEM allocator, spare
 constexpr int kProducerWarp = 16, kMmaWarp = 17, kAllocWarp = 18;
@@ -293,6 +301,7 @@ k_svr_tc(const DevRegion *__restrict__ regions, const int64_t *__restrict__ tile
                 if (j >= TC_STAGES) mbar_wait(&b_empty[s], ((j / TC_STAGES) - 1) & 1);
                 uint8_t *dst = smem + kOffB + s * TC_STAGE_BYTES;
                 if (MG_TC_ABLATE & 32) { mbar_arrive(&b_full[s]); continue; }
+                TC_STAMP(j, 0);   // copy of stage j issued
                 mbar_arrive_expect_tx(&b_full[s], TC_IMG_BYTES + TC_N * 8);
                 bulk_g2s(dst, b_img + (size_t)j * TC_IMG_BYTES, TC_IMG_BYTES, &b_full[s]);
                 bulk_g2s(dst + TC_IMG_BYTES, w_reg + (size_t)j * TC_N, TC_N * 8, &b_full[s]);
@@ -307,7 +316,9 @@ k_svr_tc(const DevRegion *__restrict__ regions, const int64_t *__restrict__ tile
             for (int j = 0; j < n_tiles; j++) {
                 const int s = j % TC_STAGES, ds = j & 1;
                 mbar_wait(&b_full[s], (j / TC_STAGES) & 1);
+                TC_STAMP(j, 1);   // operands of tile j have landed
                 if (j >= 2) mbar_wait(&d_empty[ds], ((j >> 1) - 1) & 1);
+                TC_STAMP(j, 2);   // accumulator stage free: MMAs of tile j issue now
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 const uint32_t b_hi = smem_u32(smem + kOffB + s * TC_STAGE_BYTES), b_lo = b_hi + TC_B_F_BYTES, b_i = b_hi + 2 * TC_B_F_BYTES;
                 const uint32_t d_hh = tmem_d + (uint32_t)(ds * 3 * TC_N), d_x = d_hh + TC_N, d_i = d_hh + 2 * TC_N;
@@ -339,6 +350,7 @@ k_svr_tc(const DevRegion *__restrict__ regions, const int64_t *__restrict__ tile
             const int s = j % TC_STAGES, ds = j & 1;
             mbar_wait(&b_full[s], (j / TC_STAGES) & 1);   // completed long ago; orders our reads of the stage's constants
             mbar_wait(&d_full[ds], (j >> 1) & 1);
+            if (warp == 0 && lane == 0) TC_STAMP(j, 3);   // accumulators of tile j complete (seen by epilogue warp 0)
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             const uint32_t stage_s = smem_u32(smem + kOffB + s * TC_STAGE_BYTES);
             const uint32_t sce_s = stage_s + 2 * TC_B_F_BYTES + TC_B_I_BYTES + quarter * 128, scl_s = sce_s + TC_N * 8;
@@ -356,6 +368,7 @@ k_svr_tc(const DevRegion *__restrict__ regions, const int64_t *__restrict__ tile
                     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
                     __syncwarp();
                     if (lane == 0) mbar_arrive(&d_empty[ds]);
+                    if (warp == 0 && lane == 0) TC_STAMP(j, 4);   // epilogue warp 0 has read its part of the accumulators
                 }
                 double ea[4], eb[4];
                 if (MG_TC_ABLATE & 8) {
@@ -393,6 +406,7 @@ k_svr_tc(const DevRegion *__restrict__ regions, const int64_t *__restrict__ tile
             }
             __syncwarp();
             if (lane == 0) mbar_arrive(&b_empty[s]);  // constants of the stage are consumed
+            if (warp == 0 && lane == 0) TC_STAMP(j, 5);   // epilogue warp 0 done with tile j
         }
         const double acc = acc0 + acc1;
         // the four column quarters of a row
@@ -428,6 +442,10 @@ __global__ void __launch_bounds__(256) k_lrc_weights_tc(const double *__restrict
 }
 
 }  // namespace
+
+#ifdef MG_TC_TRACE
+extern "C" int mg_tc_trace_fetch(long long *out) { return cudaMemcpyFromSymbol(out, g_tc_trace, sizeof(long long) * 64 * 8) == cudaSuccess ? 0 : -1; }
+#endif
 
 int launch_tc_setup(mg_ctx *ctx)
 {
