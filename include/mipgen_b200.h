@@ -278,6 +278,16 @@ int64_t mg_panel_format_records(mg_ctx *ctx, mg_panel *p, const mg_record_meta *
  * [1e-12, 1e15), which the record formatter leaves to the host).  Exposed for tests. */
 int mg_format_g(mg_ctx *ctx, const double *values, int64_t n, char *out32, int *len);
 
+/* ---- the FASTQ files check_copy_numbers writes for BWA (mipgen.cpp:798-840), formatted on the device --------------------------------
+ * all_sequences.fq: one read per (region, capture size descending, MIP start ascending) "@<capture>_<chr>_<start>" (mipgen.cpp:808-823);
+ * oligo_copy_count.fq: one read per (region, oligo size in the given order, start ascending) "@chr<chr>:<a>-<b>" (mipgen.cpp:824-836).
+ * chr[i] names region i's chromosome.  With buf == NULL the calls return the number of bytes needed (host arithmetic); otherwise the
+ * bytes written, or a negative status. */
+int64_t mg_format_capture_fastq(mg_ctx *ctx, const mg_region *regions, const char *const *chr, int n, int max_capture, int min_capture,
+                                int capture_increment, char *buf, int64_t cap);
+int64_t mg_format_oligo_fastq(mg_ctx *ctx, const mg_region *regions, const char *const *chr, int n, const int *oligo_sizes, int n_oligo_sizes,
+                              char *buf, int64_t cap);
+
 /* ---- one call per batch of Featurev5 objects: what tile_regions does per feature up to collapse_mips ----------
  * (mipgen.cpp:412-505: the candidate loop nest, condense_mips, collapse_mips), for a caller that keeps pick_mips
  * (mipgen.cpp:1506-1614) on the host.  Regions are walked in sub-batches of at most max_batch_candidates grid

@@ -128,6 +128,10 @@ SYMBOLS = [
     ("mg_panel_format_records", C.c_int64, [C.c_void_p, C.c_void_p, C.POINTER(MgRecordMeta), c_int64_p, C.c_int64, C.c_int, C.c_char_p,
                                             C.c_int, C.c_void_p, C.c_int64]),
     ("mg_format_g", C.c_int, [C.c_void_p, c_double_p, C.c_int64, C.c_void_p, c_int_p]),
+    ("mg_format_capture_fastq", C.c_int64, [C.c_void_p, C.POINTER(MgRegion), C.POINTER(C.c_char_p), C.c_int, C.c_int, C.c_int, C.c_int,
+                                            C.c_void_p, C.c_int64]),
+    ("mg_format_oligo_fastq", C.c_int64, [C.c_void_p, C.POINTER(MgRegion), C.POINTER(C.c_char_p), C.c_int, c_int_p, C.c_int, C.c_void_p,
+                                          C.c_int64]),
 ]
 
 _lib = None
@@ -461,6 +465,27 @@ class Context:
         ln = np.zeros(v.size, np.int32)
         self._check(self.lib.mg_format_g(self.h, _ptr(v, c_double_p), v.size, out.ctypes.data_as(C.c_void_p), _ptr(ln, c_int_p)))
         return [bytes(out[i, :ln[i]]).decode() if ln[i] >= 0 else None for i in range(v.size)]
+
+    def fastq(self, regions: Sequence[Region], chrom: str = "1", oligo: bool = False) -> bytes:
+        """check_copy_numbers' all_sequences.fq (oligo=False) / oligo_copy_count.fq (oligo=True) for the regions, formatted on the
+        device (mg_format_capture_fastq / mg_format_oligo_fastq)."""
+        arr, _keep = self._regions(regions)
+        names = (C.c_char_p * max(1, len(regions)))(*[chrom.encode()] * len(regions))
+        cfg = self.cfg
+        if oligo:
+            sizes = np.asarray(cfg.oligo_sizes, np.int32)
+            call = lambda b, cap: self.lib.mg_format_oligo_fastq(self.h, arr, names, len(regions), _ptr(sizes, c_int_p), sizes.size, b, cap)
+        else:
+            call = lambda b, cap: self.lib.mg_format_capture_fastq(self.h, arr, names, len(regions), cfg.max_capture, cfg.min_capture,
+                                                                    cfg.capture_increment, b, cap)
+        need = call(None, 0)
+        if need < 0:
+            raise MgError("fastq sizing failed (%d): %s" % (need, self.lib.mg_last_error(self.h).decode()))
+        buf = np.empty(max(1, need), np.uint8)
+        n = call(buf.ctypes.data_as(C.c_void_p), buf.size)
+        if n != need:
+            raise MgError("fastq formatting failed (%d): %s" % (n, self.lib.mg_last_error(self.h).decode()))
+        return buf[:n].tobytes()
 
     def svr_tensor_core_available(self) -> bool:
         return bool(self.lib.mg_svr_tensor_core_available(self.h))

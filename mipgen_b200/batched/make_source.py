@@ -4,12 +4,14 @@
     python make_source.py /root/reference/mipgen.cpp _build/mipgen_batched.cpp
 
 Reads the reference's mipgen.cpp WHERE IT LIES and writes a patched copy into the (git-ignored) build directory; nothing
-of the reference is stored in this repository.  Three anchored edits, each checked to match exactly once:
+of the reference is stored in this repository.  Four anchored edits, each checked to match exactly once:
 
   1. `#include "mipgen_batched.h"` before `class mipgen{`, `#include "batched_members.inc"` right after its `public:`;
   2. tile_regions (mipgen.cpp:403-556): the statements from the initialisation of current_scan_start_position (:421)
      through `collapse_mips();` (:505) become `b200_tile_feature(feature);`;
-  3. predict_value (mipgen.cpp:1948): first statement returns the device score parked by get_parameters, if any.
+  3. predict_value (mipgen.cpp:1948): first statement returns the device score parked by get_parameters, if any;
+  4. check_copy_numbers (mipgen.cpp:796-873): the loops that print all_sequences.fq / oligo_copy_count.fq (:804-838) become
+     `b200_write_fastqs(BWAFQ, ARMSFQ);` (the bwa calls and the SAM parsing that follow are untouched).
 """
 import re
 import sys
@@ -38,6 +40,13 @@ def main():
     # 3. predict_value
     m = one(r"double\s+predict_value\s*\(\s*vector<double>\s*&\s*parameters\s*,\s*svm_model\s*\*\s*model\s*\)\s*\{", t, "predict_value")
     t = t[:m.end()] + "\n\t{ double b200_score; if (mipgen_b200_take_pending_svr(&b200_score)) return b200_score; } // mipgen_b200\n" + t[m.end():]
+    # 4. check_copy_numbers (mipgen.cpp:796-873): the loops that print the two FASTQ files for BWA (:804-838)
+    a = one(r"^[ \t]*Featurev5\s*\*\s*feature;\s*for\s*\(list<Featurev5>::iterator it = features_to_scan\.begin\(\); it != features_to_scan\.end\(\); it\+\+\)\s*\{\s*"
+            r"feature = &\*it;\s*string chr = feature->chr;\s*for \(int capture_size = max_capture_size", t, "FASTQ loops of check_copy_numbers", re.M)
+    b = one(r"^[ \t]*BWAFQ\.close\(\);", t, "BWAFQ.close()", re.M)
+    if not (a.start() < b.start()):
+        sys.exit("make_source.py: FASTQ anchors out of order")
+    t = t[:a.start()] + "\tb200_write_fastqs(BWAFQ, ARMSFQ); // mipgen_b200: both FASTQ files formatted on the GPU\n" + t[b.start():]
     open(dst, "w", encoding="latin-1", newline="").write(t)
 
 

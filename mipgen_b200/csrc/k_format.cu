@@ -374,3 +374,172 @@ extern "C" int64_t mg_panel_format_records(mg_ctx *ctx, mg_panel *p, const mg_re
     cleanup();
     return total;
 }
+
+// =====================================================================================================================
+// The two FASTQ files check_copy_numbers writes for BWA (mipgen.cpp:798-840), formatted on the device:
+//   <project>.all_sequences.fq     one read per (feature, capture size, MIP start): "@<capture>_<chr>_<start>\n<seq>\n+\n###..\n"
+//   <project>.oligo_copy_count.fq  one read per (feature, oligo size, start):        "@chr<chr>:<a>-<b>\n<seq>\n+\n###..\n"
+// Records of one (feature, size) group are consecutive and their lengths differ only through the digit counts of the
+// coordinates, so every record's byte offset has a closed form: one warp per record, no prefix-sum pass.
+// =====================================================================================================================
+namespace {
+
+struct FqGroup {      // one (feature, size) run of consecutive starts
+    int64_t out_off;  // byte offset of the group's first record
+    int64_t seq_off;  // offset of the feature's sequence in the ASCII array
+    int seq_start;    // chromosome coordinate of sequence index 0
+    int first, count; // first start coordinate, number of records
+    int size;         // capture size / oligo size
+    int chr_off, chr_len;
+    int64_t rec0;     // index of the group's first record among all records of the launch
+};
+
+// sum over j < k of the decimal digit count of (x0 + j), x0 >= 1
+__host__ __device__ inline int64_t digit_sum(int64_t x0, int64_t k)
+{
+    int64_t s = k, p = 10;
+    for (int d = 1; d < 11; d++, p *= 10) {
+        const int64_t above = x0 + k - p;  // how many of x0 .. x0+k-1 are >= 10^d
+        if (above <= 0) break;
+        s += above < k ? above : k;
+    }
+    return s;
+}
+
+__host__ __device__ inline int digits_of(int64_t x)
+{
+    int n = 1;
+    while (x >= 10) { x /= 10; n++; }
+    return n;
+}
+
+template <bool kOligo>
+__global__ void __launch_bounds__(256)
+k_fastq(const FqGroup *__restrict__ groups, int n_groups, int64_t n_records, const char *__restrict__ ascii, const char *__restrict__ strings,
+        char *__restrict__ out)
+{
+    __shared__ char head_all[8][64];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    char *head = head_all[warp];
+    for (int64_t rec = (int64_t)blockIdx.x * 8 + warp; rec < n_records; rec += (int64_t)gridDim.x * 8) {
+        int lo = 0, hi = n_groups - 1;
+        while (lo < hi) {
+            const int mid = (lo + hi + 1) >> 1;
+            if (groups[mid].rec0 <= rec) lo = mid; else hi = mid - 1;
+        }
+        const FqGroup g = groups[lo];
+        const int64_t k = rec - g.rec0;
+        const int start = g.first + (int)k;
+        // fixed part of a record: '@' + separators + newline, sequence + newline, "+\n", quality + newline
+        int64_t off;
+        int hl = 0;
+        if (kOligo) {
+            const int fixed = 1 + 3 + g.chr_len + 1 + 1 + 1 + 2 * (g.size + 1) + 2;   // "@chr" chr ':' a '-' b '\n' ...
+            off = g.out_off + k * fixed + digit_sum(g.first, k) + digit_sum((int64_t)g.first + g.size - 1, k);
+            if (lane == 0) {
+                head[hl++] = '@'; head[hl++] = 'c'; head[hl++] = 'h'; head[hl++] = 'r';
+                for (int i = 0; i < g.chr_len; i++) head[hl++] = strings[g.chr_off + i];
+                head[hl++] = ':'; hl += put_int(head + hl, start); head[hl++] = '-'; hl += put_int(head + hl, start + g.size - 1); head[hl++] = '\n';
+            }
+        } else {
+            const int fixed = 1 + digits_of(g.size) + 1 + g.chr_len + 1 + 1 + 2 * (g.size + 1) + 2;   // '@' size '_' chr '_' start '\n' ...
+            off = g.out_off + k * fixed + digit_sum(g.first, k);
+            if (lane == 0) {
+                head[hl++] = '@'; hl += put_int(head + hl, g.size); head[hl++] = '_';
+                for (int i = 0; i < g.chr_len; i++) head[hl++] = strings[g.chr_off + i];
+                head[hl++] = '_'; hl += put_int(head + hl, start); head[hl++] = '\n';
+            }
+        }
+        hl = __shfl_sync(0xffffffffu, hl, 0);
+        __syncwarp();
+        char *o = out + off;
+        for (int i = lane; i < hl; i += 32) o[i] = head[i];
+        const char *seq = ascii + g.seq_off + (start - g.seq_start);
+        for (int i = lane; i < g.size; i += 32) { o[hl + i] = seq[i]; o[hl + g.size + 3 + i] = '#'; }
+        if (lane == 0) { o[hl + g.size] = '\n'; o[hl + g.size + 1] = '+'; o[hl + g.size + 2] = '\n'; o[hl + 2 * g.size + 3] = '\n'; }
+        __syncwarp();
+    }
+}
+
+// host side shared by both files
+int64_t fastq_run(mg_ctx *ctx, bool oligo, const mg_region *regions, const char *const *chr, int n, const int *sizes, int n_sizes, char *buf, int64_t cap)
+{
+    if (!ctx || n < 0 || n_sizes < 0 || (n > 0 && (!regions || !chr)) || (n_sizes > 0 && !sizes)) return MG_ERR_INVALID;
+    std::vector<FqGroup> groups;
+    std::string pool;
+    int64_t bytes = 0, records = 0, seq_total = 0;
+    std::vector<int64_t> seq_off((size_t)n);
+    for (int i = 0; i < n; i++) {
+        const mg_region &r = regions[i];
+        if (!r.seq || r.seq_len <= 0 || !chr[i]) { ctx->err = "mg_format_*_fastq: region without sequence / chromosome name"; return MG_ERR_INVALID; }
+        seq_off[(size_t)i] = seq_total;
+        seq_total += r.seq_len;
+        const int chr_off = (int)pool.size(), chr_len = (int)strlen(chr[i]);
+        pool += chr[i];
+        for (int s = 0; s < n_sizes; s++) {
+            const int size = sizes[s];
+            FqGroup g;
+            g.size = size; g.chr_off = chr_off; g.chr_len = chr_len; g.seq_off = seq_off[(size_t)i]; g.seq_start = r.seq_start;
+            if (oligo) {
+                // relative starts 0 .. len - size - 1 (mipgen.cpp:826-828)
+                g.first = r.seq_start; g.count = r.seq_len - size;
+            } else {
+                // current_mip_start from start_flanked - capture while < stop_flanked, kept if > 0 and the read fits (mipgen.cpp:811-823)
+                const int a = std::max(1, r.start_flanked - size), b = std::min(r.stop_flanked - 1, r.seq_stop - size + 1);
+                g.first = a; g.count = b - a + 1;
+                if (g.count > 0 && a < r.seq_start) { ctx->err = "mg_format_capture_fastq: a read starts before the region's sequence"; return MG_ERR_INVALID; }
+            }
+            if (g.count <= 0) continue;
+            g.out_off = bytes; g.rec0 = records;
+            const int64_t fixed = oligo ? 1 + 3 + chr_len + 1 + 1 + 1 + 2 * (size + 1) + 2 : 1 + digits_of(size) + 1 + chr_len + 1 + 1 + 2 * (size + 1) + 2;
+            bytes += (int64_t)g.count * fixed + digit_sum(g.first, g.count) + (oligo ? digit_sum((int64_t)g.first + size - 1, g.count) : 0);
+            records += g.count;
+            groups.push_back(g);
+        }
+    }
+    if (!buf) return bytes;   // sizing call
+    if (bytes > cap) { ctx->err = "mg_format_*_fastq: output buffer too small"; return MG_ERR_INVALID; }
+    if (bytes == 0) return 0;
+    if (cudaSetDevice(ctx->device) != cudaSuccess) return MG_ERR_CUDA;
+    std::vector<char> ascii((size_t)seq_total);
+    for (int i = 0; i < n; i++) memcpy(&ascii[(size_t)seq_off[(size_t)i]], regions[i].seq, (size_t)regions[i].seq_len);
+    FqGroup *d_g = nullptr; char *d_a = nullptr, *d_s = nullptr, *d_o = nullptr;
+    auto cleanup = [&]() { mg_dev_free(ctx, d_g); mg_dev_free(ctx, d_a); mg_dev_free(ctx, d_s); mg_dev_free(ctx, d_o); };
+#define Q_TRY(expr) do { cudaError_t _e = (expr); if (_e != cudaSuccess) { ctx->err = std::string(#expr) + ": " + cudaGetErrorString(_e); cudaStreamSynchronize(ctx->stream); cleanup(); return MG_ERR_CUDA; } } while (0)
+    Q_TRY(mg_dev_alloc(ctx, (void **)&d_g, groups.size() * sizeof(FqGroup)));
+    Q_TRY(mg_dev_alloc(ctx, (void **)&d_a, ascii.size()));
+    Q_TRY(mg_dev_alloc(ctx, (void **)&d_s, pool.size() + 1));
+    Q_TRY(mg_dev_alloc(ctx, (void **)&d_o, (size_t)bytes));
+    Q_TRY(cudaMemcpyAsync(d_g, groups.data(), groups.size() * sizeof(FqGroup), cudaMemcpyHostToDevice, ctx->stream));
+    Q_TRY(cudaMemcpyAsync(d_a, ascii.data(), ascii.size(), cudaMemcpyHostToDevice, ctx->stream));
+    Q_TRY(cudaMemcpyAsync(d_s, pool.data(), pool.size() + 1, cudaMemcpyHostToDevice, ctx->stream));
+    const int64_t blocks = std::min<int64_t>((records + 7) / 8, (int64_t)ctx->sm_count * 16);
+    mg_time_begin(ctx, TM_OTHER, records);
+    if (oligo) k_fastq<true><<<(unsigned)blocks, 256, 0, ctx->stream>>>(d_g, (int)groups.size(), records, d_a, d_s, d_o);
+    else k_fastq<false><<<(unsigned)blocks, 256, 0, ctx->stream>>>(d_g, (int)groups.size(), records, d_a, d_s, d_o);
+    mg_time_end(ctx);
+    Q_TRY(cudaGetLastError());
+    Q_TRY(cudaMemcpyAsync(buf, d_o, (size_t)bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    Q_TRY(cudaStreamSynchronize(ctx->stream));
+#undef Q_TRY
+    cleanup();
+    return bytes;
+}
+
+}  // namespace
+
+extern "C" int64_t mg_format_capture_fastq(mg_ctx *ctx, const mg_region *regions, const char *const *chr, int n, int max_capture, int min_capture,
+                                           int capture_increment, char *buf, int64_t cap)
+{
+    if (max_capture < min_capture || min_capture <= 0 || capture_increment < 0) return MG_ERR_INVALID;
+    std::vector<int> sizes;
+    const int inc = capture_increment == 0 ? 1 : capture_increment;  // (a zero increment would never terminate in the reference's loop)
+    for (int c = max_capture; c >= min_capture; c -= inc) sizes.push_back(c);
+    return fastq_run(ctx, false, regions, chr, n, sizes.data(), (int)sizes.size(), buf, cap);
+}
+
+extern "C" int64_t mg_format_oligo_fastq(mg_ctx *ctx, const mg_region *regions, const char *const *chr, int n, const int *oligo_sizes, int n_oligo_sizes,
+                                         char *buf, int64_t cap)
+{
+    return fastq_run(ctx, true, regions, chr, n, oligo_sizes, n_oligo_sizes, buf, cap);
+}

@@ -25,7 +25,9 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 BATCHED_CLI = os.path.join(ROOT, "mipgen_b200", "dropin", "_build", "mipgen_batched")
 needs_binaries = pytest.mark.skipif(not (os.path.exists(REF_CLI) and os.path.exists(BATCHED_CLI)),
                                     reason="reference / batched CLI not prebuilt (needs /root/reference at build time)")
-DESIGN_FILES = ["all_mips.txt", "collapsed_mips.txt", "picked_mips.txt", "snp_mips.txt"]
+DESIGN_FILES = ["all_mips.txt", "collapsed_mips.txt", "picked_mips.txt", "snp_mips.txt",
+                # check_copy_numbers' inputs for BWA (mipgen.cpp:798-840): written on the device in the batched driver
+                "all_sequences.fq", "oligo_copy_count.fq"]
 
 
 @pytest.fixture(scope="module")

@@ -115,3 +115,41 @@ def test_device_formatter_throughput_on_the_bench_panel():
     assert got.size / (t.ms_other / 1e3) / 1e9 > 5.0
     pnl.close()
     ctx.close()
+
+
+def test_fastq_files_for_bwa_equal_the_reference_loops():
+    """check_copy_numbers' two FASTQ files (mipgen.cpp:804-838) formatted on the device against a literal Python restatement of the
+    loops: capture sizes descending, MIP starts from start_flanked - capture while < stop_flanked (kept if > 0 and the read fits),
+    then every oligo size over relative starts 0 .. len - size - 1.  Coordinates crossing 9,999 -> 10,000 change the record
+    length inside a group; a region at the chromosome start exercises the start > 0 filter."""
+    cfg = panel.Config(170, 150, 5)
+    genome = panel.lcg_genome(40000, 77)
+    regions = [panel.cut_region(genome, 9990, 10080, cfg, 0, "digits"), panel.cut_region(genome, 60, 140, cfg, 0, "edge"),
+               panel.cut_region(genome, 20000, 20130, cfg, 0, "plain")]
+    ctx = mg.Context(0)
+    ctx.set_config(cfg)
+
+    def want_capture():
+        out = []
+        for r in regions:
+            for cap in cfg.captures:
+                start = r.start_flanked - cap
+                while start < r.stop_flanked:
+                    if start > 0 and start + cap - 1 <= r.seq_stop:
+                        out.append(b"@%d_chrA_%d\n%s\n+\n%s\n" % (cap, start, r.seq[start - r.seq_start:start - r.seq_start + cap], b"#" * cap))
+                    start += 1
+        return b"".join(out)
+
+    def want_oligo():
+        out = []
+        for r in regions:
+            for size in cfg.oligo_sizes:
+                for rel in range(0, len(r.seq) - size):
+                    a = r.seq_start + rel
+                    out.append(b"@chrchrA:%d-%d\n%s\n+\n%s\n" % (a, a + size - 1, r.seq[rel:rel + size], b"#" * size))
+        return b"".join(out)
+
+    got_c, got_o = ctx.fastq(regions, "chrA"), ctx.fastq(regions, "chrA", oligo=True)
+    assert got_c == want_capture() and len(got_c) > 100000
+    assert got_o == want_oligo() and len(got_o) > 100000
+    ctx.close()
