@@ -1,6 +1,6 @@
 // mipgen_batched.h -- file-scope declarations for the batched MIPgen driver (INTEGRATION.md route C).
 //
-// The batched driver is the reference's own mipgen.cpp with three anchored edits applied at BUILD time by
+// The batched driver is the reference's own mipgen.cpp with four anchored edits applied at BUILD time by
 // make_source.py (no reference code lives in this repository):
 //   1. this header is included before `class mipgen`, and batched_members.inc inside it;
 //   2. in tile_regions (mipgen.cpp:403-556) the per-feature candidate loop nest + condense_mips + collapse_mips
@@ -39,6 +39,8 @@ struct mipgen_b200_batch {
     std::vector<double> sb_logistic, sb_svr, logistic, svr;
     std::vector<uint8_t> valid;
     long n_batches = 0, n_objects = 0;
+    double t_first_tile = 0;                 // ... and when the tile phase began
+    double t_constructed = 0;                // CLOCK_MONOTONIC when `class mipgen` was constructed (start of main)
     double device_seconds = 0, setup_seconds = 0, prep_seconds = 0, objects_seconds = 0, records_seconds = 0;  // MIPGEN_B200_VERBOSE report
 };
 #endif

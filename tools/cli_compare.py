@@ -3,7 +3,9 @@
 (mipgen_b200/dropin/_build/mipgen: the same mipgen.cpp against the GPU library) and the batched caller
 (INTEGRATION.md route B: mg_panel_score + mg_panel_select + mg_format_mip_records, which writes collapsed_mips.txt
 itself) on one synthetic panel.  Outputs must be byte-identical; prints the timings as JSON.
-    python tools/cli_compare.py [n_regions] [n_sv] [svr_regions]
+    python tools/cli_compare.py [n_regions] [n_sv] [svr_regions] [quick]
+`quick` times only the silent reference run and the batched driver (twice: the first process on an idle GPU also pays the driver's
+device initialisation) -- the byte-identity of every output file, silent or not, is what tests/test_cli_batched.py checks.
 """
 import filecmp
 import json
@@ -118,6 +120,7 @@ def main():
     n_cand = sum(cfg.grid_size(r) for r in regions)
     out = {"regions": n_regions, "candidates": n_cand, "n_sv": n_sv}
     svr_regions = int(sys.argv[3]) if len(sys.argv) > 3 else max(2, n_regions // 10)
+    quick = len(sys.argv) > 4 and sys.argv[4] == "quick"
     for mode, nreg in (("logistic", n_regions), ("svr", svr_regions)):
         bed_m = bed
         if nreg != n_regions:
@@ -125,6 +128,17 @@ def main():
             panel.write_bed(bed_m, regions[:nreg])
         extra = ["-score_method", mode]
         a, ta, _ = run(REF, d, "ref_" + mode, bed_m, gdir, model, extra)
+        if quick:
+            runs = []
+            for rep in range(2):
+                e, te, elog = run(BATCHED, d, "batched_%s_%d" % (mode, rep), bed_m, gdir, model, extra)
+                same_c = all(filecmp.cmp(os.path.join(a, "p." + f), os.path.join(e, "p." + f), shallow=False)
+                             for f in ("picked_mips.txt", "collapsed_mips.txt", "snp_mips.txt"))
+                runs.append({"wall_s": round(te, 2), "speedup": round(ta / te, 1), "identical_picked_collapsed_snp": same_c,
+                             "driver_report": elog[-1] if elog else ""})
+            out[mode + "_batched_cli"] = {"regions": nreg, "candidates": sum(cfg.grid_size(r) for r in regions[:nreg]),
+                                          "reference_silent_s": round(ta, 2), "batched_silent_runs": runs}
+            continue
         b, tb, log = run(NEW, d, "b200_" + mode, bed_m, gdir, model, extra)
         same = all(filecmp.cmp(os.path.join(a, "p." + f), os.path.join(b, "p." + f), shallow=False)
                    for f in ("picked_mips.txt", "collapsed_mips.txt", "snp_mips.txt"))
@@ -144,7 +158,8 @@ def main():
         out[mode + "_batched_cli"] = {"regions": nreg, "reference_silent_s": round(ta, 2), "batched_silent_s": round(te, 2),
                                       "speedup_silent": round(ta / te, 1), "identical_picked_collapsed_snp": same_c,
                                       "reference_not_silent_s": round(tc, 2), "batched_not_silent_s": round(te2, 2),
-                                      "speedup_not_silent": round(tc / te2, 1), "identical_all_files_not_silent": same_c2}
+                                      "speedup_not_silent": round(tc / te2, 1), "identical_all_files_not_silent": same_c2,
+                                      "driver_report": elog[-1] if elog else ""}
         out[mode] = {"regions": nreg, "candidates": sum(cfg.grid_size(r) for r in regions[:nreg]), "reference_s": round(ta, 2),
                      "dropin_s": round(tb, 2), "identical_outputs": same, "shim": log[-1] if log else "",
                      "reference_not_silent_s": round(tc, 2), "batched_caller": bt,
