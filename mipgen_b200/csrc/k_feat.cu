@@ -354,7 +354,8 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, 3)
 k_feat_window(const DevConfig *__restrict__ cfg, const DevRegion *__restrict__ regions, const DevTask *__restrict__ tasks,
               int task0, int task1, const uint8_t *__restrict__ codes, const double *__restrict__ lrc_all,
               const int *__restrict__ copies, const uint32_t *__restrict__ fdesc, const double *__restrict__ logtab,
-              int64_t g_base, uint8_t *__restrict__ valid, double *__restrict__ logistic, double *__restrict__ x, int stride)
+              int64_t g_base, uint8_t *__restrict__ valid, double *__restrict__ logistic, double *__restrict__ x, int stride,
+              uint8_t *__restrict__ state, double *__restrict__ rows, const DevFact *__restrict__ fc, int ftask_base, double gamma)
 {
     extern __shared__ __align__(16) uint8_t smem_raw[];
     double *rn = reinterpret_cast<double *>(smem_raw);            // [kRecipN]
@@ -471,6 +472,7 @@ k_feat_window(const DevConfig *__restrict__ cfg, const DevRegion *__restrict__ r
                     flags = 1 | (invalid ? 2 : 0) | (fast ? 4 : 0) | (g.rc ? 8 : 0);
                 }
                 if (valid) valid[tk.g0 + goff] = (uint8_t)g.ok;
+                if (state) state[tk.g0 + goff] = (uint8_t)(!g.ok ? 0 : (invalid ? 1 : 2));
                 if (logistic) {
                     Stash st;
                     st.state = !g.ok ? 0 : (invalid ? 1 : 2);
@@ -580,6 +582,110 @@ k_feat_window(const DevConfig *__restrict__ cfg, const DevRegion *__restrict__ r
                         else val = jj == 0 ? ce : cl;
                         xrow[32 * m] = val;
                     }
+                }
+            }
+        }
+
+        // ---- row-table mode: the distinct arm / insert rows of the factored-SVR work items nested in this task ----
+        // A work item (fc->W scan starts, one capture size, one strand; k_svr_fact.cu) needs, instead of its candidates' 192-vectors,
+        //   rows [0, RA):        the arm that ends at the scan start      (+: extension [s-e, s-1], -: ligation [s-l, s-1])
+        //   rows [RA, RA+RQ):    the arm that starts at q = s + cap - sum (+: ligation, -: extension), q-indexed
+        //   rows [RA+RQ, R):     the insert [s, s + cap - sum - 1]
+        // each as its block of the feature vector (21 ratios, length, log copy | 85 ratios, scan size) with -gamma ||row||^2
+        // in the block's spare column -- exactly the tables k_svr_fact keeps in shared memory, so it fetches them with one bulk copy.
+        if (rows) {
+            const int fW = fc->W, n_ext = fc->n_ext, n_lig = fc->n_lig, n_sums = fc->n_sums, dsum = fc->max_sum - fc->min_sum;
+            const int n_sub = (tk.nsi + fW - 1) / fW;
+            const double kZeroNorm = -gamma * 0.0;
+            for (int ft = 0; ft < n_sub * tk.nci * 2; ft++) {
+                const int strand = ft & 1, cr = (ft >> 1) % tk.nci, sub = (ft >> 1) / tk.nci, ci = tk.ci0 + cr;
+                const int cap = wc.max_capture - ci * wc.inc;
+                // a capture size ruled out for the whole region (mipgen.cpp:429) scores nothing: k_svr_fact never fetches its tables
+                if (cap > r.stop_flanked - r.start_flanked + wc.max_mip_overlap && cap - wc.inc >= wc.min_capture) continue;
+                const int nsi_f = min(fW, tk.nsi - sub * fW);
+                const int nA = strand ? n_lig : n_ext, nQ = strand ? n_ext : n_lig;
+                const int RA = (nsi_f * nA + 15) & ~15, RQ = ((nsi_f + dsum) * nQ + 15) & ~15, RI = (nsi_f * n_sums + 15) & ~15;
+                double *FAg = rows + (int64_t)(tk.ft0 + (sub * wc.n_cap + ci) * 2 + strand - ftask_base) * fc->blob_doubles;
+                double *FQg = FAg + fc->cap_FA, *FIg = FQg + fc->cap_FQ, *xxg = FIg + fc->cap_FI;
+                int *jcg = reinterpret_cast<int *>(xxg + fc->cap_R);
+                const int s0 = r.first_scan + tk.si0 + sub * fW;  // the work item's first scan start (chromosome coordinate)
+                for (int row = warp; row < RA + RQ + RI; row += kWarpsPerBlock) {
+                    int role, len = 0, start = 0;  // role 0 extension arm, 1 ligation arm, 2 insert
+                    bool live;
+                    double *dst;
+                    if (row < RA) {
+                        const int s_rel = row / nA, ia = row - s_rel * nA;
+                        live = s_rel < nsi_f; role = strand ? 1 : 0;
+                        len = strand ? fc->lig_of[ia] : fc->ext_of[ia];
+                        start = s0 + s_rel - len;
+                        dst = FAg + row * FACT_LD_ARM;
+                    } else if (row < RA + RQ) {
+                        const int m = row - RA, j = m / nQ, iq = m - j * nQ;
+                        live = j < nsi_f + dsum; role = strand ? 0 : 1;
+                        len = strand ? fc->ext_of[iq] : fc->lig_of[iq];
+                        start = s0 + j + cap - fc->max_sum;
+                        dst = FQg + m * FACT_LD_ARM;
+                    } else {
+                        const int m = row - RA - RQ, s_rel = m / n_sums, is = m - s_rel * n_sums;
+                        live = s_rel < nsi_f; role = 2;
+                        len = cap - fc->sum_of[is];  // scan size
+                        start = s0 + s_rel;
+                        dst = FIg + m * FACT_LD_INS;
+                    }
+                    // the characters present: std::string::substr clamps the length (as candidate_geometry does)
+                    const int off = start - r.seq_start;
+                    live = live && len >= 0 && off >= 0 && off <= r.seq_len;
+                    const int n = live ? min(len, r.seq_len - off) : 0, a = off - span0;
+                    live = live && a >= 0 && a + n <= span_len;   // rows of scored candidates always lie inside the window's span
+                    auto ratio_of = [&](int f) {
+                        const uint32_t d = fdesc[f];
+                        const int km1 = (d >> 5) & 3;
+                        const int prow = strand ? (int)((d >> 15) & 255) : (int)((d >> 7) & 255);
+                        const int end = a + n - km1;
+                        const int cnt = (int)(uint16_t)(P[prow * stride + max(end, a)] - P[prow * stride + a]);
+                        const int den = len - km1;
+                        const double ad = (double)cnt, bd = (double)den;
+                        if (den <= 0 || den >= kRecipN) return __ddiv_rn(ad, bd);
+                        const double y = rn[den], q0 = __dmul_rn(ad, y);
+                        return __fma_rn(__fma_rn(-q0, bd, ad), y, q0);
+                    };
+                    double v[3] = {0.0, 0.0, 0.0};
+                    int code = 16;
+                    if (live && role < 2) {
+                        if (lane < 21) v[0] = ratio_of(role ? 152 + lane : lane);
+                        else if (lane == 21) v[0] = (double)len;
+                        else if (lane == 22) v[0] = r.copy_off >= 0 ? log_copy(copy_lookup(cfg, r, copies, start, len), logtab) : 0.0;
+                        if (role == 1 && n >= 2) {
+                            const uint32_t j0 = strand ? codes_s[a + n - 1] : codes_s[a], j1 = strand ? codes_s[a + n - 2] : codes_s[a + 1];
+                            if (j0 < 4 && j1 < 4) code = strand ? (int)((3 - j0) * 4 + (3 - j1)) : (int)(j0 * 4 + j1);
+                        }
+                    } else if (live) {
+#pragma unroll
+                        for (int i = 0; i < 3; i++) {
+                            const int k = lane + 32 * i;
+                            if (k < 85) v[i] = ratio_of(66 + k);
+                            else if (k == 85) v[i] = (double)len;
+                        }
+                    }
+                    double ssum = 0.0;
+#pragma unroll
+                    for (int i = 0; i < 3; i++) ssum = fma(v[i], v[i], ssum);
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) ssum += __shfl_xor_sync(0xffffffffu, ssum, o);
+                    // a non-finite feature (log10(0) = -inf copy, a zero divisor) makes every kernel value of the row 0, as in libsvm:
+                    // the row is parked at exponent -inf with finite (zero) features so the contraction stays NaN free
+                    const bool finite = fabs(ssum) <= 1.7976931348623157e308;
+                    const double nrm = !live ? kZeroNorm : (finite ? -gamma * ssum : __longlong_as_double(0xfff0000000000000LL));
+                    if (role < 2) {
+                        if (lane < FACT_LD_ARM) dst[lane] = lane == FACT_K_ARM - 1 ? nrm : (finite ? v[0] : 0.0);
+                    } else {
+#pragma unroll
+                        for (int i = 0; i < 3; i++) {
+                            const int k = lane + 32 * i;
+                            if (k < FACT_LD_INS) dst[k] = k == FACT_K_INS - 2 ? nrm : (finite ? v[i] : 0.0);
+                        }
+                    }
+                    if (lane == 0) { xxg[row] = nrm; jcg[row] = role == 1 ? code : 16; }
                 }
             }
         }
@@ -723,7 +829,7 @@ int launch_feat_setup(mg_ctx *ctx)
 }
 
 int launch_feat_grid(mg_ctx *ctx, const mg_panel *p, int task0, int task1, int64_t g_base, int64_t n_cand, uint8_t *d_valid,
-                     double *d_logistic, double *d_x)
+                     double *d_logistic, double *d_x, uint8_t *d_state, double *d_rows, int ftask_base)
 {
     if (task1 <= task0) return MG_OK;
     const size_t smem = feat_window_smem(p->pf_stride, p->span_cap, (int)ctx->cfg.ext_len.size());
@@ -734,7 +840,8 @@ int launch_feat_grid(mg_ctx *ctx, const mg_panel *p, int task0, int task1, int64
     mg_time_begin(ctx, TM_FEAT, n_cand);
     k_feat_window<<<blocks, kWarpsPerBlock * 32, smem, ctx->stream>>>(ctx->d_cfg, p->d_regions, p->d_tasks, task0, task1, p->d_codes,
                                                                       p->d_lrc, p->d_copies, ctx->d_fdesc_win, ctx->d_logcopy, g_base,
-                                                                      d_valid, d_logistic, d_x, p->pf_stride);
+                                                                      d_valid, d_logistic, d_x, p->pf_stride, d_state, d_rows, ctx->d_fact,
+                                                                      ftask_base, ctx->gamma);
     mg_time_end(ctx);
     CUDA_TRY(ctx, cudaGetLastError());
     return MG_OK;

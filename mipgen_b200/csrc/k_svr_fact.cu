@@ -23,7 +23,8 @@
 // Same FP64 arithmetic as the dense kernel per block (||x||^2 + ||s||^2 - 2 x.s, here scaled by -gamma at
 // model upload so that the contraction ends on the exponent), ~1e-13 relative agreement with libsvm;
 // work per (candidate, SV) drops from ~219 to ~35 FP64-pipe slots.
-// Row features are read from the feature rows K-feat wrote (a representative candidate per row).
+// The distinct rows' blocks come ready-made from K-feat's row-table mode (k_feat.cu: straight from its prefix-count tables, no
+// 192-vector per candidate is ever materialised): one bulk copy per work item brings them into shared memory.
 // SV blocks are re-tiled at model upload: one 20 KB bulk copy (cp.async.bulk / mbarrier) per chunk.
 #include "mg_common.cuh"
 
@@ -141,8 +142,8 @@ constexpr int kMathWarps = FACT_MATH_WARPS, kGatherWarps = FACT_GATHER_WARPS, kG
 constexpr int kUnitsPerWarp = 24;
 
 __global__ void __launch_bounds__(kThreads, 1)
-k_svr_fact(const DevFact *__restrict__ fc, const DevFTask *__restrict__ tasks, int task0, const double *__restrict__ x, int64_t g_base,
-           const uint8_t *__restrict__ valid, const double *__restrict__ blob, const double *__restrict__ w_lrc,
+k_svr_fact(const DevFact *__restrict__ fc, const DevFTask *__restrict__ tasks, int task0, const double *__restrict__ rows,
+           const uint8_t *__restrict__ cstate, const double *__restrict__ blob, const double *__restrict__ w_lrc,
            const double *__restrict__ exp2_tab, int n_sv_pad, double gamma, double rho, double zero_score, double *__restrict__ out,
            unsigned long long *__restrict__ work)
 {
@@ -168,9 +169,8 @@ k_svr_fact(const DevFact *__restrict__ fc, const DevFTask *__restrict__ tasks, i
     double *wst = slab + 2 * FACT_BLOB;     // [2][C] alpha_i * exp(-g d_lrc)
     double *etab = wst + 2 * C;             // [64]
     uint64_t *bars = reinterpret_cast<uint64_t *>(etab + 64);
-    uint64_t *slab_full = bars, *e_full = bars + 4, *e_empty = bars + 6;
-    int *rep = reinterpret_cast<int *>(bars + 8);              // [cap_R]
-    int *jc = rep + fc->cap_R;                                 // [cap_R] junction code of ligation-role rows (16: none)
+    uint64_t *slab_full = bars, *rows_full = bars + 2, *e_full = bars + 4, *e_empty = bars + 6;
+    int *jc = reinterpret_cast<int *>(bars + 8);               // [cap_R] junction code of ligation-role rows (16: none)
     uint8_t *unit_list = reinterpret_cast<uint8_t *>(jc + fc->cap_R);  // [kMathWarps][kUnitsPerWarp] units of each math warp
     uint8_t *unit_cnt = unit_list + kMathWarps * kUnitsPerWarp;        // [kMathWarps]
 
@@ -186,13 +186,13 @@ k_svr_fact(const DevFact *__restrict__ fc, const DevFTask *__restrict__ tasks, i
             mbar_init(&e_full[b], kMathWarps);
             mbar_init(&e_empty[b], kGatherWarps);
         }
+        mbar_init(rows_full, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    for (int i = threadIdx.x; i < R; i += kThreads) rep[i] = 0x7fffffff;
     __syncthreads();
 
-    // ---- phase 0 (all threads, one candidate each per round): every candidate names its three rows; the lowest
-    //      candidate index represents a row.  The result is handed to the gather thread that owns the candidate
+    // ---- phase 0 (all threads, one candidate each per round): every candidate names its three rows and reads its state
+    //      (K-feat: 0 skipped, 1 invalid, 2 scored).  The result is handed to the gather thread that owns the candidate
     //      (gather thread t owns candidates t, t + kGatherThreads, ...) through the not yet used factor table. ----
     const bool gatherer = warp >= kMathWarps && warp < kMathWarps + kGatherWarps;
     const int gt = threadIdx.x - kMathWarps * 32;
@@ -204,23 +204,14 @@ k_svr_fact(const DevFact *__restrict__ fc, const DevFTask *__restrict__ tasks, i
     int any_scored = 0;
     for (int t = threadIdx.x; t < n_c; t += kThreads) {
         const int s_rel = t / n_pairs, p = t - s_rel * n_pairs;
-        const int64_t gi = grid_index(t);
-        const uint8_t vd = valid[gi];
-        // feature 22 (extension_arm_length) is zero only in the all-zero row of an invalid candidate
-        const double f22 = vd ? x[(gi - g_base) * MG_NFEAT + 21] : 0.0;
         const int e = fc->pair_e[p], l = fc->pair_l[p], sum = e + l;
         const int ie = fc->ext_idx[e], il = fc->lig_idx[l];
         int4 ci;
         ci.x = strand ? s_rel * n_lig + il : s_rel * n_ext + ie;
         ci.y = RA + (strand ? (s_rel + fc->max_sum - sum) * n_ext + ie : (s_rel + fc->max_sum - sum) * n_lig + il);
         ci.z = RA + RQ + s_rel * n_sums + fc->sum_idx[sum - fc->min_sum];
-        ci.w = vd ? (f22 == 0.0 ? 1 : 2) : 0;
-        if (ci.w == 2) {
-            atomicMin(&rep[ci.x], t);
-            atomicMin(&rep[ci.y], t);
-            atomicMin(&rep[ci.z], t);
-            any_scored = 1;
-        }
+        ci.w = cstate[grid_index(t)];
+        any_scored |= ci.w == 2;
         cinfo[t] = ci;
     }
     // a task whose candidates are all skipped or invalid (e.g. a capture size ruled out by mipgen.cpp:429)
@@ -268,62 +259,19 @@ k_svr_fact(const DevFact *__restrict__ fc, const DevFTask *__restrict__ tasks, i
     }
     __syncthreads();
 
-    // ---- phase 1: copy each row's block out of its representative's feature row; -gamma ||row||^2.
-    //      Four rows per warp and round, so that their (dependent, latency-bound) global loads overlap ----
-    constexpr int kRB = 4;
-    for (int rb = warp * kRB; rb < R; rb += kWarps * kRB) {
-        double v[kRB][3], jv[kRB];
-        int ld[kRB], role[kRB];  // role 0 ext, 1 lig, 2 ins
-#pragma unroll
-        for (int j = 0; j < kRB; j++) {
-            const int row = rb + j;
-            const int t = row < R ? rep[row] : 0x7fffffff;
-            if (row < RA) { ld[j] = FACT_LD_ARM; role[j] = ligA ? 1 : 0; }
-            else if (row < RA + RQ) { ld[j] = FACT_LD_ARM; role[j] = ligQ ? 1 : 0; }
-            else { ld[j] = FACT_LD_INS; role[j] = 2; }
-            const double *src = t != 0x7fffffff ? x + (grid_index(t) - g_base) * MG_NFEAT : nullptr;
-#pragma unroll
-            for (int i = 0; i < 3; i++) {
-                const int k = i * 32 + lane;
-                v[j][i] = 0.0;
-                if (src && k < ld[j]) {
-                    if (role[j] == 0) v[j][i] = k < 22 ? src[k] : (k == 22 ? src[190] : 0.0);
-                    else if (role[j] == 1) v[j][i] = k < 22 ? src[152 + k] : (k == 22 ? src[191] : 0.0);
-                    else v[j][i] = k < 86 ? src[66 + k] : 0.0;
-                }
-            }
-            jv[j] = (src && role[j] == 1 && lane < 16) ? src[174 + lane] : 0.0;  // junction one-hot 175..190
-        }
-#pragma unroll
-        for (int j = 0; j < kRB; j++) {
-            const int row = rb + j;
-            if (row >= R) break;
-            double *dst = row < RA ? FA + row * FACT_LD_ARM : row < RA + RQ ? FQ + (row - RA) * FACT_LD_ARM : FI + (row - RA - RQ) * FACT_LD_INS;
-            double ssum = 0.0;
-#pragma unroll
-            for (int i = 0; i < 3; i++) ssum = fma(v[j][i], v[j][i], ssum);
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) ssum += __shfl_xor_sync(0xffffffffu, ssum, o);
-            // a non-finite feature (log10(0) = -inf copy) makes every kernel value of the row 0, as in libsvm:
-            // park the row at exponent -inf with finite (zero) features so the contraction stays NaN free
-            const bool finite = fabs(ssum) <= 1.7976931348623157e308;
-            // -gamma ||row||^2 rides in the block's spare column (the SV blocks hold 1 there), so the contraction adds it
-            const double nrm = finite ? -gamma * ssum : __longlong_as_double(0xfff0000000000000LL);
-            const int kstar = role[j] == 2 ? FACT_K_INS - 2 : FACT_K_ARM - 1;
-#pragma unroll
-            for (int i = 0; i < 3; i++) {
-                const int k = i * 32 + lane;
-                if (k < ld[j]) dst[k] = k == kstar ? nrm : (finite ? v[j][i] : 0.0);
-            }
-            if (lane == 0) xx[row] = nrm;
-            int code = 16;
-            if (jv[j] == 1.0) code = lane;
-#pragma unroll
-            for (int o = 8; o > 0; o >>= 1) code = min(code, __shfl_xor_sync(0xffffffffu, code, o));
-            if (lane == 0) jc[row] = role[j] == 1 ? code : 16;
-        }
+    // ---- phase 1: the row tables of this work item (FA | FQ | FI | xx, then jc), as K-feat wrote them: bulk copies ----
+    if (threadIdx.x == 0) {
+        const double *src = rows + (int64_t)blockIdx.x * fc->blob_doubles;
+        const uint32_t nFA = (uint32_t)fc->cap_FA * 8, nFQ = (uint32_t)fc->cap_FQ * 8, nFI = (uint32_t)fc->cap_FI * 8, nX = (uint32_t)fc->cap_R * 8,
+                       nJ = (uint32_t)((fc->cap_R * 4 + 15) & ~15);
+        mbar_arrive_expect_tx(rows_full, nFA + nFQ + nFI + nX + nJ);
+        bulk_g2s(FA, src, nFA, rows_full);
+        bulk_g2s(FQ, src + fc->cap_FA, nFQ, rows_full);
+        bulk_g2s(FI, src + fc->cap_FA + fc->cap_FQ, nFI, rows_full);
+        bulk_g2s(xx, src + fc->cap_FA + fc->cap_FQ + fc->cap_FI, nX, rows_full);
+        bulk_g2s(jc, src + fc->cap_FA + fc->cap_FQ + fc->cap_FI + fc->cap_R, nJ, rows_full);
     }
-    __syncthreads();
+    mbar_wait(rows_full, 0);
 
     // The SV blob (and the lrc weights) of chunk ch + 2 is fetched by one gather thread as soon as every math warp
     // has delivered chunk ch (e_full): the math warps arrive there after their last read of that blob buffer.
@@ -481,12 +429,12 @@ int launch_lrc_weights(mg_ctx *ctx, const mg_panel *p, double *d_w)
     return MG_OK;
 }
 
-int launch_svr_fact(mg_ctx *ctx, const mg_panel *p, int ftask0, int ftask1, const double *d_x, int64_t g_base, int64_t n_cand,
-                    const uint8_t *d_valid, const double *d_w, double *d_out)
+int launch_svr_fact(mg_ctx *ctx, const mg_panel *p, int ftask0, int ftask1, const double *d_rows, int64_t n_cand,
+                    const uint8_t *d_state, const double *d_w, double *d_out)
 {
     if (ftask1 <= ftask0) return MG_OK;
     mg_time_begin(ctx, TM_SVR, n_cand);
-    k_svr_fact<<<ftask1 - ftask0, kThreads, ctx->fact_smem, ctx->stream>>>(ctx->d_fact, p->d_ftasks, ftask0, d_x, g_base, d_valid,
+    k_svr_fact<<<ftask1 - ftask0, kThreads, ctx->fact_smem, ctx->stream>>>(ctx->d_fact, p->d_ftasks, ftask0, d_rows, d_state,
                                                                          ctx->d_fact_blob, d_w, ctx->d_exp2tab, ctx->n_sv_pad, ctx->gamma,
                                                                          ctx->rho, ctx->zero_score, d_out, ctx->d_work);
     mg_time_end(ctx);

@@ -295,7 +295,7 @@ extern "C" void mg_destroy(mg_ctx *ctx)
     for (auto e : ctx->ev_free) cudaEventDestroy(e);
     if (ctx->sw_a) { cudaEventDestroy(ctx->sw_a); cudaEventDestroy(ctx->sw_b); }
     free_model(ctx);
-    cudaFree(ctx->d_x); cudaFree(ctx->d_fdesc); cudaFree(ctx->d_fdesc_win); cudaFree(ctx->d_logcopy); cudaFree(ctx->d_exp2tab); cudaFree(ctx->d_exp2tab256); cudaFree(ctx->d_cfg); cudaFree(ctx->d_fact); cudaFree(ctx->d_work);
+    cudaFree(ctx->d_x); cudaFree(ctx->d_rows); cudaFree(ctx->d_fdesc); cudaFree(ctx->d_fdesc_win); cudaFree(ctx->d_logcopy); cudaFree(ctx->d_exp2tab); cudaFree(ctx->d_exp2tab256); cudaFree(ctx->d_cfg); cudaFree(ctx->d_fact); cudaFree(ctx->d_work);
     cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
@@ -437,6 +437,9 @@ extern "C" int mg_set_config(mg_ctx *ctx, const mg_config *c)
             for (size_t i = 0; i < exts.size(); i++) f->ext_idx[exts[i]] = (int)i;
             for (size_t i = 0; i < ligs.size(); i++) f->lig_idx[ligs[i]] = (int)i;
             for (size_t i = 0; i < sums.size(); i++) f->sum_idx[sums[i] - h.min_sum] = (int)i;
+            for (size_t i = 0; i < exts.size(); i++) f->ext_of[i] = exts[i];
+            for (size_t i = 0; i < ligs.size(); i++) f->lig_of[i] = ligs[i];
+            for (size_t i = 0; i < sums.size(); i++) f->sum_of[i] = sums[i];
             for (int i = 0; i < c->n_pairs; i++) { f->pair_e[i] = h.ext_len[i]; f->pair_l[i] = h.lig_len[i]; }
             f->n_pairs = c->n_pairs; f->n_cap = h.n_cap; f->n_ext = (int)exts.size(); f->n_lig = (int)ligs.size();
             f->n_sums = (int)sums.size(); f->min_sum = h.min_sum; f->max_sum = h.max_sum;
@@ -454,7 +457,7 @@ extern "C" int mg_set_config(mg_ctx *ctx, const mg_config *c)
                 size_t doubles = (size_t)f->cap_FA + f->cap_FQ + f->cap_FI + f->cap_R + 2 * (size_t)f->cap_R * (FACT_C + 1) + 2 * FACT_BLOB +
                                  2 * FACT_C + 64;
                 size_t bytes = doubles * 8 + 64 + (size_t)f->cap_R * 8 + FACT_MATH_WARPS * 25 + 64;  // + mbarriers, rep[] and jc[] ints, unit lists
-                if (bytes <= FACT_SMEM_LIMIT) { f->W = W; ctx->fact_ok = true; ctx->fact_W = W; ctx->fact_smem = bytes; }
+                if (bytes <= FACT_SMEM_LIMIT) { f->W = W; ctx->fact_ok = true; ctx->fact_W = W; ctx->fact_smem = bytes; f->blob_doubles = FACT_ROWS_DOUBLES(*f); }
             }
         }
         if (ctx->fact_ok) { e = cudaMemcpy(ctx->d_fact, f, sizeof *f, cudaMemcpyHostToDevice); ctx->h_fact = *f; }
@@ -674,6 +677,21 @@ static int ensure_x(mg_ctx *ctx, int64_t rows)
     return MG_OK;
 }
 
+// row tables of the factored-SVR work items in flight: at most kMaxRowsBytes of them at a time
+static const size_t kMaxRowsBytes = (size_t)2 << 30;
+
+static int ensure_rows(mg_ctx *ctx, size_t items)
+{
+    if (items <= ctx->rows_cap) return MG_OK;
+    cudaStreamSynchronize(ctx->stream);
+    cudaFree(ctx->d_rows);
+    ctx->d_rows = nullptr;
+    ctx->rows_cap = 0;
+    CUDA_TRY(ctx, cudaMalloc(&ctx->d_rows, items * (size_t)ctx->h_fact.blob_doubles * 8));
+    ctx->rows_cap = items;
+    return MG_OK;
+}
+
 // ---------------------------------------------------------------------------
 // svm_predict on dense rows
 // ---------------------------------------------------------------------------
@@ -846,7 +864,7 @@ extern "C" void mg_panel_destroy(mg_panel *p)
     mg_dev_free(c, p->d_ftasks); mg_dev_free(c, p->d_w); mg_dev_free(c, p->d_w_tc);
     mg_dev_free(c, p->d_regions); mg_dev_free(c, p->d_tasks); mg_dev_free(c, p->d_codes); mg_dev_free(c, p->d_lrc); mg_dev_free(c, p->d_copies);
     mg_dev_free(c, p->d_maskpf); mg_dev_free(c, p->d_snppf); mg_dev_free(c, p->d_unmap); mg_dev_free(c, p->d_ascii);
-    mg_dev_free(c, p->d_valid); mg_dev_free(c, p->d_logistic); mg_dev_free(c, p->d_svr); mg_dev_free(c, p->d_feat);
+    mg_dev_free(c, p->d_valid); mg_dev_free(c, p->d_state); mg_dev_free(c, p->d_logistic); mg_dev_free(c, p->d_svr); mg_dev_free(c, p->d_feat);
     delete p;
 }
 
@@ -911,7 +929,7 @@ extern "C" int mg_panel_create(mg_ctx *ctx, const mg_region *regions, int n, mg_
         for (int i = 0; i < n; i++)
             for (int si = 0; si < p->h_regions[i].n_scan; si += W) {
                 DevTask t;
-                t.region = i; t.si0 = si; t.nsi = std::min(W, p->h_regions[i].n_scan - si); t.pad = 0;
+                t.region = i; t.si0 = si; t.nsi = std::min(W, p->h_regions[i].n_scan - si); t.ft0 = 0;
                 t.ci0 = 0; t.nci = n_cap;
                 t.g0 = p->h_regions[i].grid_off + (int64_t)si * per_scan;
                 p->task_start.push_back((int)p->h_tasks.size());
@@ -940,6 +958,8 @@ extern "C" int mg_panel_create(mg_ctx *ctx, const mg_region *regions, int n, mg_
                         }
             }
             p->ftask_start[p->h_windows.size()] = (int)p->h_ftasks.size();
+            for (size_t k = 0; k < p->h_windows.size(); k++)   // K-feat's row-table mode addresses the work items nested in a window
+                for (int u = p->task_start[k]; u < p->task_start[k + 1]; u++) p->h_tasks[u].ft0 = p->ftask_start[k];
         }
         p->span_cap = W + ctx->cfg.max_arm + ctx->cfg.max_capture - ctx->cfg.min_arm + 4;
         int words = (p->span_cap + 2) / 2;
@@ -1066,11 +1086,29 @@ extern "C" int mg_panel_score(mg_ctx *ctx, mg_panel *p, int want)
     // windows [w0, w1) <-> candidates [g0, g1)
     auto svr_range = [&](int w0, int w1, const double *xbuf, int64_t g0, int64_t g1) {
         if (tc) return launch_svr_tc(ctx, p, xbuf, g0, g1, p->d_valid, p->d_w_tc, p->d_svr);
-        if (fact) return launch_svr_fact(ctx, p, p->ftask_start[w0], p->ftask_start[w1], xbuf, g0, g1 - g0, p->d_valid, p->d_w, p->d_svr);
         return launch_svr(ctx, xbuf, g1 - g0, p->d_valid + g0, p->d_svr + g0);
     };
+    auto end_of = [&](int w) { return w < n_win ? p->h_windows[w].g0 : p->n_cand; };
     if (!w_svr && !w_feat) {
         rc = launch_feat_grid(ctx, p, 0, n_tasks, 0, p->n_cand, p->d_valid, w_log ? p->d_logistic : nullptr, nullptr);
+    } else if (fact) {
+        // Factored SVR: K-feat hands over the distinct arm / insert rows of every work item (row-table mode) and the grid
+        // points' states; no 192-vector is materialised unless the caller asked for the features themselves.
+        if (w_feat) rc = launch_feat_grid(ctx, p, 0, n_tasks, 0, p->n_cand, p->d_valid, w_log ? p->d_logistic : nullptr, p->d_feat);
+        if (!p->d_state) CUDA_TRY(ctx, mg_dev_alloc(ctx, (void **)&p->d_state, (size_t)p->n_cand));
+        const size_t max_items = std::max<size_t>(1, kMaxRowsBytes / ((size_t)ctx->h_fact.blob_doubles * 8));
+        int w0 = 0;
+        while (w0 < n_win && rc == MG_OK) {
+            int w1 = w0 + 1;
+            while (w1 < n_win && (size_t)(p->ftask_start[w1 + 1] - p->ftask_start[w0]) <= max_items) w1++;
+            const int64_t g0 = p->h_windows[w0].g0, g1 = end_of(w1);
+            const int f0 = p->ftask_start[w0], f1 = p->ftask_start[w1];
+            if ((rc = ensure_rows(ctx, (size_t)(f1 - f0))) != MG_OK) return rc;
+            rc = launch_feat_grid(ctx, p, p->task_start[w0], p->task_start[w1], g0, g1 - g0, p->d_valid,
+                                  (w_log && !w_feat) ? p->d_logistic : nullptr, nullptr, p->d_state, ctx->d_rows, f0);
+            if (rc == MG_OK) rc = launch_svr_fact(ctx, p, f0, f1, ctx->d_rows, g1 - g0, p->d_state, p->d_w, p->d_svr);
+            w0 = w1;
+        }
     } else if (w_feat) {
         rc = launch_feat_grid(ctx, p, 0, n_tasks, 0, p->n_cand, p->d_valid, w_log ? p->d_logistic : nullptr, p->d_feat);
         if (rc == MG_OK && w_svr) rc = svr_range(0, n_win, p->d_feat, 0, p->n_cand);
@@ -1082,7 +1120,6 @@ extern "C" int mg_panel_score(mg_ctx *ctx, mg_panel *p, int want)
         while (w0 < n_win && rc == MG_OK) {
             const int64_t g0 = p->h_windows[w0].g0;
             int w1 = w0 + 1;
-            auto end_of = [&](int w) { return w < n_win ? p->h_windows[w].g0 : p->n_cand; };
             while (w1 < n_win && end_of(w1 + 1) - g0 <= target) w1++;
             const int64_t g1 = end_of(w1);
             if ((rc = ensure_x(ctx, g1 - g0)) != MG_OK) return rc;

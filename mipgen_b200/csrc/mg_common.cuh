@@ -49,7 +49,7 @@ struct DevTask {
     int region;      // index into DevRegion[]
     int si0, nsi;    // first scan index of the window, number of scan starts
     int ci0, nci;    // capture-size indices [ci0, ci0 + nci)
-    int pad;
+    int ft0;         // index of the first factored-SVR work item nested in the window (row-table mode of K-feat)
 };
 
 // one explicit candidate (strand-oriented codes in a packed buffer)
@@ -150,8 +150,13 @@ struct DevFact {
     int n_pairs, n_cap, n_ext, n_lig, n_sums, min_sum, max_sum, W;
     int cap_FA, cap_FQ, cap_FI, cap_R;   // shared-memory capacities in doubles / rows
     int ext_idx[FACT_MAX_LEN], lig_idx[FACT_MAX_LEN], sum_idx[FACT_MAX_SPAN];
+    int ext_of[FACT_MAX_LEN], lig_of[FACT_MAX_LEN], sum_of[FACT_MAX_SPAN];   // the inverse maps: index -> arm length / arm sum
     int pair_e[MG_MAX_PAIRS], pair_l[MG_MAX_PAIRS];
+    int blob_doubles;   // stride of one work item's row tables in the K-feat -> K-svr hand-off buffer (FACT_ROWS_DOUBLES)
 };
+// row tables of one factored-SVR work item as K-feat writes them and K-svr bulk-copies them into shared memory:
+// FA[cap_FA] | FQ[cap_FQ] | FI[cap_FI] | xx[cap_R] (doubles), then jc[cap_R] (ints); stride rounded up to 128 bytes
+#define FACT_ROWS_DOUBLES(f) ((((f).cap_FA + (f).cap_FQ + (f).cap_FI + (f).cap_R) + ((f).cap_R + 1) / 2 + 15) & ~15)
 
 // one factored-SVR work item: W scan starts of one region, one capture size, one strand
 struct DevFTask {
@@ -214,6 +219,8 @@ struct mg_ctx {
     // workspace
     double *d_x = nullptr;      // feature rows of the chunk in flight
     size_t x_rows_cap = 0;
+    double *d_rows = nullptr;   // row tables of the factored-SVR work items in flight (K-feat writes, K-svr reads)
+    size_t rows_cap = 0;        // in work items
     // freed device blocks kept for reuse (the per-call buffers of mg_score_regions / mg_score_candidates)
     std::vector<CachedBlock> pool;
     std::vector<CachedBlock> live;
@@ -257,6 +264,7 @@ struct mg_panel {
     uint8_t *d_unmap = nullptr;    // [n_cap][seq_len] per region that declares unmappable MIP starts, or null
     bool has_sel_inputs = false;   // some region carries masked_seq / snp / unmappable
     uint8_t *d_valid = nullptr;
+    uint8_t *d_state = nullptr;   // per grid point: 0 skipped, 1 invalid (N / '-' in an arm), 2 scored -- what the factored SVR reads
     double *d_logistic = nullptr;
     double *d_svr = nullptr;
     double *d_feat = nullptr;      // only when features are fetched for the whole panel
@@ -292,8 +300,10 @@ int launch_encode(mg_ctx *ctx, const char *d_ascii, uint8_t *d_codes, int64_t n)
 int launch_lrc(mg_ctx *ctx, const uint8_t *d_codes, int n, int denom, double *d_out44);
 // grid front-end: any of valid/logistic/x may be null; x rows are written at row (g - g_base).
 // tasks [task0, task1) hold n_cand consecutive candidates starting at global index g_base
+// Row-table mode (d_rows != null): instead of feature rows, the distinct arm / insert rows of the factored-SVR work items
+// nested in the tasks are written to d_rows (work item ftask_base first) and every grid point's state to d_state.
 int launch_feat_grid(mg_ctx *ctx, const mg_panel *p, int task0, int task1, int64_t g_base, int64_t n_cand, uint8_t *d_valid,
-                     double *d_logistic, double *d_x);
+                     double *d_logistic, double *d_x, uint8_t *d_state = nullptr, double *d_rows = nullptr, int ftask_base = 0);
 int launch_feat_setup(mg_ctx *ctx);
 // explicit front-end
 int launch_feat_explicit(mg_ctx *ctx, const DevCand *d_cands, const uint8_t *d_codes, const double *d_lrc,
@@ -308,8 +318,9 @@ int launch_select(mg_ctx *ctx, const mg_panel *p, const int64_t *d_scan_off, con
 int launch_gather(mg_ctx *ctx, const int64_t *d_idx, int64_t n, const double *d_a, double *d_out_a, const double *d_b, double *d_out_b);
 int launch_count_valid(mg_ctx *ctx, const uint8_t *d_valid, int64_t n, unsigned long long *d_count);
 int launch_lrc_weights(mg_ctx *ctx, const mg_panel *p, double *d_w);
-int launch_svr_fact(mg_ctx *ctx, const mg_panel *p, int ftask0, int ftask1, const double *d_x, int64_t g_base, int64_t n_cand,
-                    const uint8_t *d_valid, const double *d_w, double *d_out);
+// work items [ftask0, ftask1): their row tables are d_rows[0 ..) in order, the grid points' states d_state[] (panel-wide)
+int launch_svr_fact(mg_ctx *ctx, const mg_panel *p, int ftask0, int ftask1, const double *d_rows, int64_t n_cand,
+                    const uint8_t *d_state, const double *d_w, double *d_out);
 int mg_upload_lrc_tables(mg_ctx *ctx, const uint8_t *k, const uint8_t *code);
 // tensor-core SVR (k_svr_tc.cu)
 int launch_tc_setup(mg_ctx *ctx);
