@@ -186,6 +186,10 @@ int mg_panel_create(mg_ctx *ctx, const mg_region *regions, int n, mg_panel **out
 void mg_panel_destroy(mg_panel *p);
 int64_t mg_panel_candidates(const mg_panel *p);
 int64_t mg_panel_valid_candidates(const mg_panel *p); /* statically valid grid points */
+/* Bytes of arm / insert row tables K-feat hands to the factored SVR per scoring pass (the distinct rows of every work item:
+ * 192 B per arm row, 704 B per insert row, 12 B of norm + junction code each); 0 when the factored form does not apply.
+ * This, not 1,536 B per candidate, is what the SVR path moves through HBM between its two kernels. */
+int64_t mg_panel_row_table_bytes(const mg_panel *p);
 /* Launch the kernels for the whole panel on the context's stream (asynchronous). */
 int mg_panel_score(mg_ctx *ctx, mg_panel *p, int want);
 /* Copy results back (synchronous).  features may be NULL. */

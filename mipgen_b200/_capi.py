@@ -102,6 +102,7 @@ SYMBOLS = [
     ("mg_panel_create", C.c_int, [C.c_void_p, C.POINTER(MgRegion), C.c_int, C.POINTER(C.c_void_p)]),
     ("mg_panel_destroy", None, [C.c_void_p]),
     ("mg_panel_candidates", C.c_int64, [C.c_void_p]),
+    ("mg_panel_row_table_bytes", C.c_int64, [C.c_void_p]),
     ("mg_panel_valid_candidates", C.c_int64, [C.c_void_p]),
     ("mg_panel_score", C.c_int, [C.c_void_p, C.c_void_p, C.c_int]),
     ("mg_panel_fetch", C.c_int, [C.c_void_p, C.c_void_p, c_ubyte_p, c_double_p, c_double_p, c_double_p]),
@@ -330,6 +331,10 @@ class Panel:
 
     def valid_candidates(self) -> int:
         return int(self.ctx.lib.mg_panel_valid_candidates(self.h))
+
+    def row_table_bytes(self) -> int:
+        """Bytes of arm / insert row tables K-feat hands to the factored SVR per scoring pass (mg_panel_row_table_bytes)."""
+        return int(self.ctx.lib.mg_panel_row_table_bytes(self.h))
 
     def score(self, want: int) -> None:
         """Launch the kernels for the whole panel (asynchronous on the context's stream)."""

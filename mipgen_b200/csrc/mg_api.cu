@@ -682,13 +682,14 @@ static const size_t kMaxRowsBytes = (size_t)2 << 30;
 
 static int ensure_rows(mg_ctx *ctx, size_t items)
 {
-    if (items <= ctx->rows_cap) return MG_OK;
+    const size_t bytes = items * (size_t)ctx->h_fact.blob_doubles * 8;   // the stride changes with the configuration
+    if (bytes <= ctx->rows_cap) return MG_OK;
     cudaStreamSynchronize(ctx->stream);
     cudaFree(ctx->d_rows);
     ctx->d_rows = nullptr;
     ctx->rows_cap = 0;
-    CUDA_TRY(ctx, cudaMalloc(&ctx->d_rows, items * (size_t)ctx->h_fact.blob_doubles * 8));
-    ctx->rows_cap = items;
+    CUDA_TRY(ctx, cudaMalloc(&ctx->d_rows, bytes));
+    ctx->rows_cap = bytes;
     return MG_OK;
 }
 
@@ -955,6 +956,11 @@ extern "C" int mg_panel_create(mg_ctx *ctx, const mg_region *regions, int n, mg_
                             f.region = t.region; f.si0 = t.si0 + si; f.nsi = std::min(ctx->fact_W, t.nsi - si);
                             f.ci = ci; f.strand = strand; f.pad = 0;
                             p->h_ftasks.push_back(f);
+                            const DevFact &hf = ctx->h_fact;
+                            const int64_t arm_rows = (int64_t)f.nsi * (strand ? hf.n_lig : hf.n_ext) +
+                                                     (int64_t)(f.nsi + hf.max_sum - hf.min_sum) * (strand ? hf.n_ext : hf.n_lig);
+                            const int64_t ins_rows = (int64_t)f.nsi * hf.n_sums;
+                            p->row_table_bytes += arm_rows * FACT_LD_ARM * 8 + ins_rows * FACT_LD_INS * 8 + (arm_rows + ins_rows) * 12;
                         }
             }
             p->ftask_start[p->h_windows.size()] = (int)p->h_ftasks.size();
@@ -1032,6 +1038,7 @@ extern "C" int mg_panel_create(mg_ctx *ctx, const mg_region *regions, int n, mg_
 }
 
 extern "C" int64_t mg_panel_candidates(const mg_panel *p) { return p ? p->n_cand : 0; }
+extern "C" int64_t mg_panel_row_table_bytes(const mg_panel *p) { return p ? p->row_table_bytes : 0; }
 
 // a panel caches grid offsets, windows and task lists derived from the config it was created under
 static const char *const kStalePanel = "the panel was created under an earlier mg_set_config: create it again";

@@ -110,9 +110,11 @@ __host__ __device__ inline uint32_t fd_pack(uint32_t kind, uint32_t part, uint32
 // factored SVR (k_svr_fact.cu): block sizes, padded strides, per-chunk blob layout
 // ---------------------------------------------------------------------------
 #define FACT_C 16          // support vectors per chunk
+#ifndef FACT_MATH_WARPS
 #define FACT_MATH_WARPS 11
 #define FACT_GATHER_WARPS 5
 #define FACT_CPT 3                                      // candidates per gather thread
+#endif
 #define FACT_THREADS ((FACT_MATH_WARPS + FACT_GATHER_WARPS) * 32)       // 16 warps: 128 registers per thread
 #define FACT_K_ARM 24      // 21 arm ratios + arm length + log copy, padded to a multiple of 4 (either role)
 #define FACT_K_INS 88      // 86 insert features
@@ -220,7 +222,7 @@ struct mg_ctx {
     double *d_x = nullptr;      // feature rows of the chunk in flight
     size_t x_rows_cap = 0;
     double *d_rows = nullptr;   // row tables of the factored-SVR work items in flight (K-feat writes, K-svr reads)
-    size_t rows_cap = 0;        // in work items
+    size_t rows_cap = 0;        // in bytes
     // freed device blocks kept for reuse (the per-call buffers of mg_score_regions / mg_score_candidates)
     std::vector<CachedBlock> pool;
     std::vector<CachedBlock> live;
@@ -248,6 +250,7 @@ struct mg_panel {
     DevTask *d_tasks = nullptr;
     std::vector<DevFTask> h_ftasks;     // factored-SVR tasks, grouped by K-feat window
     std::vector<int> ftask_start;       // [n_windows+1] first factored task of each window
+    int64_t row_table_bytes = 0;        // distinct rows of all factored tasks, in bytes (see mg_panel_row_table_bytes)
     DevFTask *d_ftasks = nullptr;
     double *d_w = nullptr;              // [n_regions][n_sv_pad] alpha * exp(-g d_lrc)
     int w_n_sv_pad = 0;

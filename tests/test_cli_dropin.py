@@ -54,6 +54,19 @@ def workspace(oracle):
     return dict(dir=d, gdir=gdir, bed=bed, model=model)
 
 
+def first_difference(a, b):
+    """For assertion messages: the first line where two output files differ."""
+    with open(a, errors="replace") as fa, open(b, errors="replace") as fb:
+        for k, (x, y) in enumerate(zip(fa, fb)):
+            if x != y:
+                return "line %d:\n  ref: %s\n  new: %s" % (k + 1, x.rstrip()[:400], y.rstrip()[:400])
+    return "one file is a prefix of the other"
+
+
+def same_file(a, b, what):
+    assert filecmp.cmp(a, b, shallow=False), "%s differs; %s" % (what, first_difference(a, b))
+
+
 def run_cli(binary, ws, name, extra, env_extra=None):
     run = os.path.join(ws["dir"], name)
     os.makedirs(run)
@@ -92,7 +105,7 @@ def test_dropin_cli_with_arm_copy_numbers_other_than_one(workspace, mode):
     ref_dir, _ = run_cli(REF_CLI, workspace, "ref_copies_" + mode, flags, env)
     new_dir, log = run_cli(DROPIN_CLI, workspace, "b200_copies_" + mode, flags, env)
     for f in OUTPUTS:
-        assert filecmp.cmp(os.path.join(ref_dir, "p." + f), os.path.join(new_dir, "p." + f), shallow=False), "%s differs" % f
+        same_file(os.path.join(ref_dir, "p." + f), os.path.join(new_dir, "p." + f), f)
     copies = [l.split("\t")[5] for l in open(os.path.join(ref_dir, "p.all_mips.txt")) if not l.startswith(">")]
     assert sum(c != "1" for c in copies) > 100, "the stub must have produced arm copies other than 1"
     line = [l for l in log.splitlines() if "device batches" in l][-1]
@@ -109,7 +122,7 @@ def test_dropin_cli_writes_identical_files(workspace, case):
     for f in OUTPUTS:
         a, b = os.path.join(ref_dir, "p." + f), os.path.join(new_dir, "p." + f)
         assert os.path.getsize(a) > 200 or f == "snp_mips.txt", f
-        assert filecmp.cmp(a, b, shallow=False), "%s differs in %s" % (f, case)
+        same_file(a, b, "%s in %s" % (f, case))
     # the work really went through device batches, not per-candidate calls
     line = [l for l in log.splitlines() if "device batches" in l][-1]
     batches = int(line.split("device batches")[1].split(",")[0])

@@ -177,6 +177,26 @@ def test_factored_svr_matches_dense_and_oracle(ctx, oracle):
         assert np.isfinite(dense[v1.astype(bool)]).all() and np.isnan(dense[~v1.astype(bool)]).all()
 
 
+def test_row_table_workspace_follows_the_configuration(ctx, oracle):
+    """The K-feat -> K-svr row-table workspace is reused between calls; its per-work-item stride depends on the arm table, so a
+    context that goes from a narrow arm table to a wide one with the same number of work items must re-size it (a run of the
+    drop-in CLI does exactly this: one mg_set_config per batch)."""
+    d = tmpdir()
+    narrow = small_config((45,), 162, 152, 5)
+    wide = panel.Config(162, 152, 5, 30, *panel.default_arm_pairs((40, 41, 42, 43, 44, 45)))
+    _g, regions = synthetic_regions(oracle, wide, 3, 60, 120, 91)
+    for cfg in (narrow, wide, narrow):
+        model = random_model(oracle, cfg, 64, 3, os.path.join(d, "m%d.model" % len(cfg.ext_len)))
+        ctx.set_config(cfg)
+        ctx.load_svr_model(model)
+        assert ctx.svr_factored_available() > 0
+        _o, valid, _l, got, _f = ctx.score_regions(regions, mg.MG_WANT_SVR)
+        h = oracle.svm_load_model(model)
+        want = np.concatenate([oracle.grid_region(r, cfg, h, want_logistic=False, want_svr=True)[2] for r in regions])
+        oracle.svm_free(h)
+        assert rel_err(got, want) <= SVR_RTOL
+
+
 def test_region_grid_chunked_svr_equals_feature_path(ctx, oracle):
     """SVR through the chunked workspace path == SVR computed while features are kept."""
     cfg = small_config((40, 45))
