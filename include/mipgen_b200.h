@@ -44,6 +44,7 @@ extern "C" {
 #define MG_ERR_NOMODEL (-4) /* SVR requested before a model was loaded */
 #define MG_ERR_NOCONFIG (-5)/* grid call before mg_set_config */
 #define MG_ERR_NOMEM (-6)
+#define MG_ERR_UNSUPPORTED (-7) /* the device formatter leaves this input to the host one (score magnitude, record length) */
 
 /* what to compute (bit mask) */
 #define MG_WANT_LOGISTIC 1 /* SVMipv4::get_score                        */
@@ -278,6 +279,15 @@ typedef struct {
 } mg_record_meta;
 int64_t mg_panel_format_records(mg_ctx *ctx, mg_panel *p, const mg_record_meta *meta, const int64_t *idx, int64_t n, int which,
                                 const char *universal_middle, int first_index, char *buf, int64_t cap);
+/* all_mips.txt of a scored panel, written on the device: the records of every candidate the tile loop enumerates, in its order
+ * (mipgen.cpp:426-497 with the score-dependent shortcuts of lines 430, 434, 494 replayed per scan start by K-replay; sp->method,
+ * sp->heuristic and sp->upper_score_limit drive them, mixed mode prints logistic scores as mipgen.cpp:467-468 does), numbered
+ * first_index, first_index + 1, ...  The text is handed to `sink` in consecutive pieces (return non-zero from it to abort);
+ * records_per_region[n_regions] (may be NULL) receives each region's record count.  Returns the bytes produced or a negative
+ * status (MG_ERR_UNSUPPORTED: see above; regions with TRF / SNP / mappability inputs are refused like mg_panel_format_records). */
+typedef int (*mg_text_sink)(void *user, const char *text, int64_t len);
+int64_t mg_panel_format_enumerated(mg_ctx *ctx, mg_panel *p, const mg_record_meta *meta, const mg_select_params *sp,
+                                   const char *universal_middle, int first_index, int64_t *records_per_region, mg_text_sink sink, void *user);
 /* printf("%g") of n doubles on the device, 32 bytes per value in out32 (not NUL-terminated), lengths in len (-1: magnitude outside
  * [1e-12, 1e15), which the record formatter leaves to the host).  Exposed for tests. */
 int mg_format_g(mg_ctx *ctx, const double *values, int64_t n, char *out32, int *len);
@@ -314,6 +324,12 @@ int mg_tile_sizes(const mg_config *cfg, const mg_region *regions, int n, int64_t
  * mipgen.cpp:467-468) and may be NULL (score only: scan_best / pos_best are not written). */
 int mg_tile_regions(mg_ctx *ctx, const mg_region *regions, int n, int want, const mg_select_params *sp,
                     int64_t max_batch_candidates, mg_tile_result *out);
+
+/* mg_tile_regions that also writes all_mips.txt on the device: meta[i] describes region i; the text of the sub-batches reaches
+ * the sink in region order while the winners are being computed (one context: record numbers run through the whole list). */
+int mg_tile_regions_records(mg_ctx *ctx, const mg_region *regions, int n, int want, const mg_select_params *sp,
+                            int64_t max_batch_candidates, mg_tile_result *out, const mg_record_meta *meta, const char *universal_middle,
+                            int first_index, int64_t *records_per_region, mg_text_sink sink, void *user);
 
 /* ---- the same over several GPUs of one box ---------------------------------------------------------
  * Regions are independent (mipgen.cpp:412-525), so they are partitioned over the contexts by longest-processing-time

@@ -53,6 +53,9 @@ class MgRecordMeta(C.Structure):
     _fields_ = [("chr", C.c_char_p), ("label", C.c_char_p), ("feature_start", C.c_int), ("feature_stop", C.c_int)]
 
 
+MG_TEXT_SINK = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_int64)   # mg_text_sink
+
+
 class MgTileResult(C.Structure):
     _fields_ = [("scan_best", c_int64_p), ("pos_best", c_int64_p), ("scan_best_logistic", c_double_p),
                 ("scan_best_svr", c_double_p), ("valid", c_ubyte_p), ("logistic", c_double_p), ("svr", c_double_p)]
@@ -128,6 +131,11 @@ SYMBOLS = [
     ("mg_panel_gather", C.c_int, [C.c_void_p, C.c_void_p, c_int64_p, C.c_int64, c_double_p, c_double_p]),
     ("mg_panel_format_records", C.c_int64, [C.c_void_p, C.c_void_p, C.POINTER(MgRecordMeta), c_int64_p, C.c_int64, C.c_int, C.c_char_p,
                                             C.c_int, C.c_void_p, C.c_int64]),
+    ("mg_panel_format_enumerated", C.c_int64, [C.c_void_p, C.c_void_p, C.POINTER(MgRecordMeta), C.POINTER(MgSelectParams), C.c_char_p, C.c_int,
+                                               c_int64_p, MG_TEXT_SINK, C.c_void_p]),
+    ("mg_tile_regions_records", C.c_int, [C.c_void_p, C.POINTER(MgRegion), C.c_int, C.c_int, C.POINTER(MgSelectParams), C.c_int64,
+                                          C.POINTER(MgTileResult), C.POINTER(MgRecordMeta), C.c_char_p, C.c_int, c_int64_p, MG_TEXT_SINK,
+                                          C.c_void_p]),
     ("mg_format_g", C.c_int, [C.c_void_p, c_double_p, C.c_int64, C.c_void_p, c_int_p]),
     ("mg_format_capture_fastq", C.c_int64, [C.c_void_p, C.POINTER(MgRegion), C.POINTER(C.c_char_p), C.c_int, C.c_int, C.c_int, C.c_int,
                                             C.c_void_p, C.c_int64]),
@@ -383,6 +391,31 @@ class Panel:
         if n < 0:
             raise MgError("mg_panel_format_records failed (%d): %s" % (n, self.ctx.lib.mg_last_error(self.ctx.h).decode()))
         return out[:n]
+
+    def format_enumerated(self, regions: Sequence[Region], method: int, upper: float, heuristic: bool = True, chrom: str = "1",
+                          first_index: int = 1, middle: Optional[str] = None):
+        """all_mips.txt of the scored panel written on the device (mg_panel_format_enumerated): the records of every candidate the
+        tile loop enumerates, in its order.  Returns (bytes, records_per_region)."""
+        meta = (MgRecordMeta * max(1, len(regions)))()
+        keep = []
+        for i, r in enumerate(regions):
+            lab = r.label.encode()
+            keep.append(lab)
+            meta[i] = MgRecordMeta(chrom.encode(), lab, r.start_flanked, r.stop_flanked)
+        mid = (middle if middle is not None else universal_middle()).encode()
+        sp = MgSelectParams(method, int(heuristic), 0.0, upper, 75, 20, 0.5)
+        pieces = []
+
+        def sink(_user, text, n):
+            pieces.append(C.string_at(text, n))
+            return 0
+
+        per = np.zeros(max(1, len(regions)), np.int64)
+        cb = MG_TEXT_SINK(sink)
+        n = self.ctx.lib.mg_panel_format_enumerated(self.ctx.h, self.h, meta, C.byref(sp), mid, first_index, _ptr(per, c_int64_p), cb, None)
+        if n < 0:
+            raise MgError("mg_panel_format_enumerated failed (%d): %s" % (n, self.ctx.lib.mg_last_error(self.ctx.h).decode()))
+        return b"".join(pieces), per[:len(regions)]
 
     def select(self, regions: Sequence[Region], method: int, lower: float, upper: float, heuristic: bool = True,
                max_arm_copy: int = 75, target_arm_copy: int = 20, masked_arm_threshold: float = 0.5):

@@ -38,6 +38,9 @@ struct mipgen_b200_batch {
     std::vector<int64_t> grid_off, scan_off, pos_off, scan_best, pos_best;
     std::vector<double> sb_logistic, sb_svr, logistic, svr;
     std::vector<uint8_t> valid;
+    bool device_records = false;             // this batch's all_mips.txt records were written on the device:
+    std::vector<char> text;                  //   the text of all its features, in order (flushed with the batch's first feature)
+    std::vector<int64_t> records_per_region; //   and how many records each feature contributed
     long n_batches = 0, n_objects = 0;
     double t_first_tile = 0;                 // ... and when the tile phase began
     double t_constructed = 0;                // CLOCK_MONOTONIC when `class mipgen` was constructed (start of main)

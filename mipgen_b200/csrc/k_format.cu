@@ -296,11 +296,11 @@ extern "C" int mg_format_g(mg_ctx *ctx, const double *values, int64_t n, char *o
     return MG_OK;
 }
 
-extern "C" int64_t mg_panel_format_records(mg_ctx *ctx, mg_panel *p, const mg_record_meta *meta, const int64_t *idx, int64_t n, int which,
-                                           const char *universal_middle, int first_index, char *buf, int64_t cap)
+// n records given by panel-global grid indices (on the host, or already on the device) -> text.  Either into buf (capacity cap) or,
+// with buf == NULL, into *text (resized).  Returns the bytes written or a negative status.
+static int64_t format_records_core(mg_ctx *ctx, mg_panel *p, const mg_record_meta *meta, const int64_t *idx, bool idx_on_device, int64_t n, int which,
+                                   const char *universal_middle, int first_index, char *buf, int64_t cap, std::vector<char> *text)
 {
-    if (!ctx || !p || p->ctx != ctx || !meta || n < 0 || (n > 0 && (!idx || !buf)) || !universal_middle) return MG_ERR_INVALID;
-    if (p->cfg_serial != ctx->cfg_serial) { ctx->err = "the panel was created under an earlier mg_set_config: create it again"; return MG_ERR_INVALID; }
     const double *d_score = which == 1 ? (p->has_svr ? p->d_svr : nullptr) : (p->has_logistic ? p->d_logistic : nullptr);
     if (!d_score) { ctx->err = "mg_panel_format_records: the panel has not been scored with the requested scores"; return MG_ERR_INVALID; }
     if (p->has_sel_inputs) {
@@ -308,7 +308,7 @@ extern "C" int64_t mg_panel_format_records(mg_ctx *ctx, mg_panel *p, const mg_re
         return MG_ERR_INVALID;
     }
     if (!p->d_ascii) { ctx->err = "mg_panel_format_records: the panel keeps no ASCII sequences"; return MG_ERR_INVALID; }
-    if (n == 0) return 0;
+    if (n == 0) { if (text) text->clear(); return 0; }
     if (cudaSetDevice(ctx->device) != cudaSuccess) return MG_ERR_CUDA;
     // per-region strings
     std::vector<FmtRegion> fr((size_t)p->n_regions);
@@ -322,19 +322,23 @@ extern "C" int64_t mg_panel_format_records(mg_ctx *ctx, mg_panel *p, const mg_re
     const int mid_len = (int)strlen(universal_middle);
     pool += universal_middle;
     const int mid_off = (int)pool.size() - mid_len;
-    FmtRegion *d_fr = nullptr; char *d_str = nullptr, *d_out = nullptr; int64_t *d_idx = nullptr, *d_off = nullptr; FmtRec *d_rec = nullptr; int *d_len = nullptr, *d_status = nullptr;
-    auto cleanup = [&]() { mg_dev_free(ctx, d_fr); mg_dev_free(ctx, d_str); mg_dev_free(ctx, d_out); mg_dev_free(ctx, d_idx); mg_dev_free(ctx, d_off); mg_dev_free(ctx, d_rec); mg_dev_free(ctx, d_len); mg_dev_free(ctx, d_status); };
+    FmtRegion *d_fr = nullptr; char *d_str = nullptr, *d_out = nullptr; int64_t *d_idx_own = nullptr, *d_off = nullptr; FmtRec *d_rec = nullptr; int *d_len = nullptr, *d_status = nullptr;
+    auto cleanup = [&]() { mg_dev_free(ctx, d_fr); mg_dev_free(ctx, d_str); mg_dev_free(ctx, d_out); mg_dev_free(ctx, d_idx_own); mg_dev_free(ctx, d_off); mg_dev_free(ctx, d_rec); mg_dev_free(ctx, d_len); mg_dev_free(ctx, d_status); };
 #define R_TRY(expr) do { cudaError_t _e = (expr); if (_e != cudaSuccess) { ctx->err = std::string(#expr) + ": " + cudaGetErrorString(_e); cudaStreamSynchronize(ctx->stream); cleanup(); return MG_ERR_CUDA; } } while (0)
     R_TRY(mg_dev_alloc(ctx, (void **)&d_fr, fr.size() * sizeof(FmtRegion)));
     R_TRY(mg_dev_alloc(ctx, (void **)&d_str, pool.size() + 1));
-    R_TRY(mg_dev_alloc(ctx, (void **)&d_idx, (size_t)n * 8));
     R_TRY(mg_dev_alloc(ctx, (void **)&d_off, (size_t)(n + 1) * 8));
     R_TRY(mg_dev_alloc(ctx, (void **)&d_rec, (size_t)n * sizeof(FmtRec)));
     R_TRY(mg_dev_alloc(ctx, (void **)&d_len, (size_t)n * 4));
     R_TRY(mg_dev_alloc(ctx, (void **)&d_status, 4));
     R_TRY(cudaMemcpyAsync(d_fr, fr.data(), fr.size() * sizeof(FmtRegion), cudaMemcpyHostToDevice, ctx->stream));
     R_TRY(cudaMemcpyAsync(d_str, pool.data(), pool.size() + 1, cudaMemcpyHostToDevice, ctx->stream));
-    R_TRY(cudaMemcpyAsync(d_idx, idx, (size_t)n * 8, cudaMemcpyHostToDevice, ctx->stream));
+    const int64_t *d_idx = idx;
+    if (!idx_on_device) {
+        R_TRY(mg_dev_alloc(ctx, (void **)&d_idx_own, (size_t)n * 8));
+        R_TRY(cudaMemcpyAsync(d_idx_own, idx, (size_t)n * 8, cudaMemcpyHostToDevice, ctx->stream));
+        d_idx = d_idx_own;
+    }
     R_TRY(cudaMemsetAsync(d_status, 0, 4, ctx->stream));
     mg_time_begin(ctx, TM_OTHER, n);
     k_fmt_len<<<(unsigned)((n + 127) / 128), 128, 0, ctx->stream>>>(ctx->d_cfg, p->d_regions, p->n_regions, d_fr, p->d_copies, d_idx, n, d_score, mid_len,
@@ -350,15 +354,16 @@ extern "C" int64_t mg_panel_format_records(mg_ctx *ctx, mg_panel *p, const mg_re
         ctx->err = status == 1 ? "mg_panel_format_records: a grid index lies outside its region's grid or sequence"
                                : "mg_panel_format_records: a score outside [1e-12, 1e15) in magnitude (format it on the host)";
         cleanup();
-        return MG_ERR_INVALID;
+        return status == 1 ? MG_ERR_INVALID : MG_ERR_UNSUPPORTED;
     }
     std::vector<int64_t> off((size_t)n + 1);
     off[0] = 0;
     int longest = 0;
     for (int64_t i = 0; i < n; i++) { off[(size_t)i + 1] = off[(size_t)i] + len[(size_t)i]; longest = std::max(longest, len[(size_t)i]); }
     const int64_t total = off[(size_t)n];
-    if (longest > kFmtStage) { ctx->err = "mg_panel_format_records: a record exceeds the staging buffer (capture size too large)"; cleanup(); return MG_ERR_INVALID; }
-    if (total > cap) { ctx->err = "mg_panel_format_records: output buffer too small"; cleanup(); return MG_ERR_INVALID; }
+    if (longest > kFmtStage) { ctx->err = "mg_panel_format_records: a record exceeds the staging buffer (capture size too large)"; cleanup(); return MG_ERR_UNSUPPORTED; }
+    if (buf && total > cap) { ctx->err = "mg_panel_format_records: output buffer too small"; cleanup(); return MG_ERR_INVALID; }
+    if (!buf) { text->resize((size_t)total); buf = text->data(); }
     R_TRY(mg_dev_alloc(ctx, (void **)&d_out, (size_t)std::max<int64_t>(total, 1)));
     R_TRY(cudaMemcpyAsync(d_off, off.data(), (size_t)(n + 1) * 8, cudaMemcpyHostToDevice, ctx->stream));
     mg_time_begin(ctx, TM_OTHER, n);
@@ -369,10 +374,78 @@ extern "C" int64_t mg_panel_format_records(mg_ctx *ctx, mg_panel *p, const mg_re
     R_TRY(cudaGetLastError());
     R_TRY(cudaMemcpyAsync(buf, d_out, (size_t)total, cudaMemcpyDeviceToHost, ctx->stream));
     R_TRY(cudaStreamSynchronize(ctx->stream));
-#undef R_TRY
-#undef F_TRY
     cleanup();
     return total;
+}
+
+extern "C" int64_t mg_panel_format_records(mg_ctx *ctx, mg_panel *p, const mg_record_meta *meta, const int64_t *idx, int64_t n, int which,
+                                           const char *universal_middle, int first_index, char *buf, int64_t cap)
+{
+    if (!ctx || !p || p->ctx != ctx || !meta || n < 0 || (n > 0 && (!idx || !buf)) || !universal_middle) return MG_ERR_INVALID;
+    if (p->cfg_serial != ctx->cfg_serial) { ctx->err = "the panel was created under an earlier mg_set_config: create it again"; return MG_ERR_INVALID; }
+    return format_records_core(ctx, p, meta, idx, false, n, which, universal_middle, first_index, buf, cap, nullptr);
+}
+
+// all_mips.txt of a scored panel (mipgen.cpp:474, 488): K-replay finds the grid points the tile loop enumerates, in its order
+// (count per scan start -> prefix sum -> fill), the record kernels print them; the text goes to the sink in pieces of at most
+// kEnumPiece records so that neither side ever holds more than ~1 GB of it.
+extern "C" int64_t mg_panel_format_enumerated(mg_ctx *ctx, mg_panel *p, const mg_record_meta *meta, const mg_select_params *sp,
+                                              const char *universal_middle, int first_index, int64_t *records_per_region, mg_text_sink sink,
+                                              void *user)
+{
+    if (!ctx || !p || p->ctx != ctx || !meta || !sp || !universal_middle || !sink) return MG_ERR_INVALID;
+    if (p->cfg_serial != ctx->cfg_serial) { ctx->err = "the panel was created under an earlier mg_set_config: create it again"; return MG_ERR_INVALID; }
+    const int which = sp->method == 1 ? 1 : 0;   // mixed mode enumerates and prints with the logistic score (mipgen.cpp:467-468)
+    const double *d_score = which == 1 ? (p->has_svr ? p->d_svr : nullptr) : (p->has_logistic ? p->d_logistic : nullptr);
+    if (!d_score) { ctx->err = "mg_panel_format_enumerated: the panel has not been scored with the scores this method prints"; return MG_ERR_INVALID; }
+    if (cudaSetDevice(ctx->device) != cudaSuccess) return MG_ERR_CUDA;
+    const int n = p->n_regions;
+    std::vector<int64_t> so((size_t)n + 1, 0);
+    for (int i = 0; i < n; i++) so[(size_t)i + 1] = so[(size_t)i] + p->h_regions[i].n_scan;
+    const int64_t total_scan = so[(size_t)n];
+    for (int i = 0; i < n && records_per_region; i++) records_per_region[i] = 0;
+    if (total_scan == 0) return 0;
+    int64_t *d_so = nullptr, *d_off = nullptr, *d_idx = nullptr;
+    int *d_count = nullptr;
+    auto cleanup = [&]() { mg_dev_free(ctx, d_so); mg_dev_free(ctx, d_off); mg_dev_free(ctx, d_idx); mg_dev_free(ctx, d_count); };
+#define E_TRY(expr) do { cudaError_t _e = (expr); if (_e != cudaSuccess) { ctx->err = std::string(#expr) + ": " + cudaGetErrorString(_e); cudaStreamSynchronize(ctx->stream); cleanup(); return MG_ERR_CUDA; } } while (0)
+    E_TRY(mg_dev_alloc(ctx, (void **)&d_so, (size_t)(n + 1) * 8));
+    E_TRY(mg_dev_alloc(ctx, (void **)&d_off, (size_t)total_scan * 8));
+    E_TRY(mg_dev_alloc(ctx, (void **)&d_count, (size_t)total_scan * 4));
+    E_TRY(cudaMemcpyAsync(d_so, so.data(), (size_t)(n + 1) * 8, cudaMemcpyHostToDevice, ctx->stream));
+    int rc = launch_replay(ctx, p, d_so, total_scan, d_score, sp, d_count, nullptr, nullptr);
+    if (rc != MG_OK) { cleanup(); return rc; }
+    std::vector<int> count((size_t)total_scan);
+    E_TRY(cudaMemcpyAsync(count.data(), d_count, (size_t)total_scan * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    E_TRY(cudaStreamSynchronize(ctx->stream));
+    std::vector<int64_t> off((size_t)total_scan);
+    int64_t n_rec = 0;
+    for (int i = 0; i < n; i++)
+        for (int64_t t = so[(size_t)i]; t < so[(size_t)i + 1]; t++) {
+            off[(size_t)t] = n_rec;
+            n_rec += count[(size_t)t];
+            if (records_per_region) records_per_region[i] += count[(size_t)t];
+        }
+    if (n_rec == 0) { cleanup(); return 0; }
+    if ((int64_t)first_index + n_rec > 0x7fffffff) { ctx->err = "mg_panel_format_enumerated: record numbers exceed the int range"; cleanup(); return MG_ERR_INVALID; }
+    E_TRY(mg_dev_alloc(ctx, (void **)&d_idx, (size_t)n_rec * 8));
+    E_TRY(cudaMemcpyAsync(d_off, off.data(), (size_t)total_scan * 8, cudaMemcpyHostToDevice, ctx->stream));
+    rc = launch_replay(ctx, p, d_so, total_scan, d_score, sp, nullptr, d_off, d_idx);
+    if (rc != MG_OK) { cudaStreamSynchronize(ctx->stream); cleanup(); return rc; }
+    E_TRY(cudaStreamSynchronize(ctx->stream));  // off[] is read by the copy above
+#undef E_TRY
+    const int64_t kEnumPiece = (int64_t)2 << 20;
+    std::vector<char> text;
+    int64_t bytes = 0;
+    for (int64_t r0 = 0; r0 < n_rec; r0 += kEnumPiece) {
+        const int64_t m = std::min(kEnumPiece, n_rec - r0);
+        const int64_t got = format_records_core(ctx, p, meta, d_idx + r0, true, m, which, universal_middle, first_index + (int)r0, nullptr, 0, &text);
+        if (got < 0) { cleanup(); return got; }
+        if (sink(user, text.data(), got) != 0) { ctx->err = "mg_panel_format_enumerated: the sink reported an error"; cleanup(); return MG_ERR_INVALID; }
+        bytes += got;
+    }
+    cleanup();
+    return bytes;
 }
 
 // =====================================================================================================================

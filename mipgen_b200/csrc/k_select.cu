@@ -231,6 +231,61 @@ __global__ void __launch_bounds__(256) k_count_valid(const uint8_t *__restrict__
     if ((threadIdx.x & 31) == 0 && c) atomicAdd(count, (unsigned long long)c);
 }
 
+
+// K-replay: which grid points does the tile loop enumerate (and print to all_mips.txt, mipgen.cpp:474, 488), in its order?
+// The enumeration order is the grid order, so per scan start the answer is a subset of its (capture, pair) combinations, both
+// strands of each: the same replay of the score-dependent shortcuts as K-condense's pass 1.  kFill = false counts them per scan
+// start; kFill = true writes their panel-global grid indices at the scan start's offset (exclusive prefix sum of the counts).
+template <bool kFill>
+__global__ void __launch_bounds__(128)
+k_replay(const DevConfig *__restrict__ cfg, const DevRegion *__restrict__ regions, const int64_t *__restrict__ scan_off, int n_regions,
+         int64_t total_scan, const uint8_t *__restrict__ valid, const double *__restrict__ score, SelParams sp, int *__restrict__ count,
+         const int64_t *__restrict__ out_off, int64_t *__restrict__ out_idx)
+{
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= total_scan) return;
+    int lo = 0, hi = n_regions - 1;  // region of this scan start
+    while (lo < hi) {
+        const int mid = (lo + hi + 1) >> 1;
+        if (scan_off[mid] <= t) lo = mid; else hi = mid - 1;
+    }
+    const DevRegion r = regions[lo];
+    const int si = (int)(t - scan_off[lo]);
+    const int n_cap = cfg->n_cap, n_pairs = cfg->n_pairs, inc = cfg->inc;
+    const int64_t base = r.grid_off + (int64_t)si * n_cap * n_pairs * 2;
+    int n = 0;
+    int64_t at = kFill ? out_off[t] : 0;
+    double previous_best = 0.0;  // :426
+    for (int ci = 0; ci < n_cap; ci++) {
+        const int cap = cfg->max_capture - ci * inc;
+        if (cap > r.stop_flanked - r.start_flanked + cfg->max_mip_overlap && cap - inc >= cfg->min_capture) continue;  // :429
+        if (previous_best > sp.upper) continue;                                                                       // :430
+        int p = 0;
+        while (p < n_pairs) {
+            const int sum = cfg->ext_len[p] + cfg->lig_len[p];
+            int q = p;
+            while (q < n_pairs && cfg->ext_len[q] + cfg->lig_len[q] == sum) q++;
+            if (!(previous_best > sp.upper && sum != cfg->min_sum)) {  // :434
+                int prev_minus = 0, prev_plus = 0;                     // ints in the reference (:435-436)
+                for (int k = p; k < q; k++) {
+                    const int64_t idx = base + (int64_t)(ci * n_pairs + k) * 2;
+                    if (!valid[idx]) continue;                         // :443-444
+                    const double plus = score[idx], minus = score[idx + 1];
+                    if (kFill) { out_idx[at] = idx; out_idx[at + 1] = idx + 1; at += 2; }
+                    n += 2;
+                    const bool stop = sp.method == 0 && sp.heuristic && plus < prev_plus && minus < prev_minus;  // :494
+                    previous_best = minus > plus ? minus : plus;       // :495
+                    prev_minus = __double2int_rz(minus);               // :496
+                    prev_plus = __double2int_rz(plus);                 // :497
+                    if (stop) break;
+                }
+            }
+            p = q;
+        }
+    }
+    if (!kFill) count[t] = n;
+}
+
 }  // namespace
 
 int launch_select(mg_ctx *ctx, const mg_panel *p, const int64_t *d_scan_off, const int64_t *d_pos_off, int64_t total_scan,
@@ -279,6 +334,25 @@ int launch_count_valid(mg_ctx *ctx, const uint8_t *d_valid, int64_t n, unsigned 
     if (n <= 0) return MG_OK;
     const int64_t blocks = std::min<int64_t>((n + 255) / 256, (int64_t)ctx->sm_count * 16);
     k_count_valid<<<(unsigned)blocks, 256, 0, ctx->stream>>>(d_valid, n, d_count);
+    CUDA_TRY(ctx, cudaGetLastError());
+    return MG_OK;
+}
+
+int launch_replay(mg_ctx *ctx, const mg_panel *p, const int64_t *d_scan_off, int64_t total_scan, const double *d_score, const mg_select_params *msp,
+                  int *d_count, const int64_t *d_out_off, int64_t *d_out_idx)
+{
+    if (total_scan <= 0) return MG_OK;
+    SelParams sp;
+    sp.method = msp->method; sp.heuristic = msp->heuristic; sp.lower = msp->lower_score_limit; sp.upper = msp->upper_score_limit;
+    sp.max_arm_copy = msp->max_arm_copy; sp.target_arm_copy = msp->target_arm_copy; sp.masked_thr = msp->masked_arm_threshold;
+    mg_time_begin(ctx, TM_OTHER, total_scan);
+    if (d_out_idx)
+        k_replay<true><<<(unsigned)((total_scan + 127) / 128), 128, 0, ctx->stream>>>(ctx->d_cfg, p->d_regions, d_scan_off, p->n_regions, total_scan,
+                                                                                       p->d_valid, d_score, sp, nullptr, d_out_off, d_out_idx);
+    else
+        k_replay<false><<<(unsigned)((total_scan + 127) / 128), 128, 0, ctx->stream>>>(ctx->d_cfg, p->d_regions, d_scan_off, p->n_regions, total_scan,
+                                                                                        p->d_valid, d_score, sp, d_count, nullptr, nullptr);
+    mg_time_end(ctx);
     CUDA_TRY(ctx, cudaGetLastError());
     return MG_OK;
 }

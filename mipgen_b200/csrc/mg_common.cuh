@@ -318,6 +318,9 @@ int launch_svr_setup(mg_ctx *ctx);
 int launch_fact_setup(mg_ctx *ctx);
 int launch_select(mg_ctx *ctx, const mg_panel *p, const int64_t *d_scan_off, const int64_t *d_pos_off, int64_t total_scan,
                   int64_t total_pos, const double *d_score, const mg_select_params *sp, int64_t *d_scan_best, int64_t *d_pos_best);
+// K-replay: d_out_idx == null counts the enumerated grid points per scan start into d_count, otherwise fills their indices
+int launch_replay(mg_ctx *ctx, const mg_panel *p, const int64_t *d_scan_off, int64_t total_scan, const double *d_score, const mg_select_params *sp,
+                  int *d_count, const int64_t *d_out_off, int64_t *d_out_idx);
 int launch_gather(mg_ctx *ctx, const int64_t *d_idx, int64_t n, const double *d_a, double *d_out_a, const double *d_b, double *d_out_b);
 int launch_count_valid(mg_ctx *ctx, const uint8_t *d_valid, int64_t n, unsigned long long *d_count);
 int launch_lrc_weights(mg_ctx *ctx, const mg_panel *p, double *d_w);

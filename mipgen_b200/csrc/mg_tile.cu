@@ -61,6 +61,16 @@ namespace {
 
 struct Offsets { std::vector<int64_t> g, s, p; };
 
+// optional: all_mips.txt records of every region, written on the device and streamed to the caller in region order
+struct TileRecords {
+    const mg_record_meta *meta;
+    const char *universal_middle;
+    int first_index;
+    int64_t *records_per_region;
+    mg_text_sink sink;
+    void *user;
+};
+
 int check_args(mg_ctx *ctx, int want, const mg_select_params *sp, const mg_tile_result *out)
 {
     if (!ctx->has_cfg) { ctx->err = "mg_set_config has not been called"; return MG_ERR_NOCONFIG; }
@@ -77,8 +87,11 @@ int check_args(mg_ctx *ctx, int want, const mg_select_params *sp, const mg_tile_
 
 // regions[mine[*]] through one context, results at the caller's offsets
 int tile_core(mg_ctx *ctx, const mg_region *regions, const std::vector<int> &mine, int want, const mg_select_params *sp, int64_t batch_cap,
-              const mg_tile_result *out, const Offsets &off)
+              const mg_tile_result *out, const Offsets &off, const TileRecords *rec = nullptr)
 {
+    int next_index = rec ? rec->first_index : 0;
+    std::vector<mg_record_meta> meta;
+    std::vector<int64_t> per_region;
     if (batch_cap <= 0) batch_cap = (int64_t)1 << 26;
     want &= MG_WANT_LOGISTIC | MG_WANT_SVR;
     std::vector<mg_region> batch;
@@ -128,6 +141,17 @@ int tile_core(mg_ctx *ctx, const mg_region *regions, const std::vector<int> &min
                 }
             }
         }
+        if (rc == MG_OK && rec) {
+            // `mine` is the identity here (one context), so the sub-batches -- and the text -- come in region order
+            meta.assign(rec->meta + mine[k0], rec->meta + mine[k0] + batch.size());
+            per_region.assign(batch.size(), 0);
+            const int64_t got = mg_panel_format_enumerated(ctx, p, meta.data(), sp, rec->universal_middle, next_index, per_region.data(), rec->sink, rec->user);
+            if (got < 0) rc = (int)got;
+            for (size_t j = 0; j < batch.size() && rc == MG_OK; j++) {
+                if (rec->records_per_region) rec->records_per_region[mine[k0 + j]] = per_region[j];
+                next_index += (int)per_region[j];
+            }
+        }
         if (rc == MG_OK && (out->valid || out->logistic || out->svr)) {
             cudaError_t e = cudaSetDevice(ctx->device);
             for (size_t j = 0; j < batch.size() && e == cudaSuccess; j++) {
@@ -158,7 +182,7 @@ int config_of(const mg_ctx *ctx, mg_config *c)
 }
 
 int tile_multi(mg_ctx *const *ctxs, int n_ctx, const mg_region *regions, int n, int want, const mg_select_params *sp, int64_t batch_cap,
-               const mg_tile_result *out, int64_t *out_offsets)
+               const mg_tile_result *out, int64_t *out_offsets, const TileRecords *rec = nullptr)
 {
     if (!ctxs || n_ctx <= 0 || n < 0 || (n > 0 && !regions) || !out) return MG_ERR_INVALID;
     for (int d = 0; d < n_ctx; d++) {
@@ -184,7 +208,7 @@ int tile_multi(mg_ctx *const *ctxs, int n_ctx, const mg_region *regions, int n, 
     if (n_ctx > 1 && mg_partition_regions(&cfg, regions, n, n_ctx, owner.data()) != MG_OK) return MG_ERR_INVALID;
     std::vector<std::vector<int>> mine((size_t)n_ctx);
     for (int i = 0; i < n; i++) mine[(size_t)owner[i]].push_back(i);
-    if (n_ctx == 1) return tile_core(ctxs[0], regions, mine[0], want, sp, batch_cap, out, off);
+    if (n_ctx == 1) return tile_core(ctxs[0], regions, mine[0], want, sp, batch_cap, out, off, rec);
     std::vector<int> rcs((size_t)n_ctx, MG_OK);
     std::vector<std::thread> th;
     for (int d = 0; d < n_ctx; d++)
@@ -202,6 +226,16 @@ extern "C" int mg_tile_regions(mg_ctx *ctx, const mg_region *regions, int n, int
 {
     mg_ctx *one[1] = {ctx};
     return tile_multi(one, 1, regions, n, want, sp, max_batch_candidates, out, nullptr);
+}
+
+extern "C" int mg_tile_regions_records(mg_ctx *ctx, const mg_region *regions, int n, int want, const mg_select_params *sp,
+                                       int64_t max_batch_candidates, mg_tile_result *out, const mg_record_meta *meta, const char *universal_middle,
+                                       int first_index, int64_t *records_per_region, mg_text_sink sink, void *user)
+{
+    if (!ctx || !sp || !meta || !universal_middle || !sink) return MG_ERR_INVALID;
+    TileRecords rec = {meta, universal_middle, first_index, records_per_region, sink, user};
+    mg_ctx *one[1] = {ctx};
+    return tile_multi(one, 1, regions, n, want, sp, max_batch_candidates, out, nullptr, &rec);
 }
 
 extern "C" int mg_tile_regions_multi(mg_ctx *const *ctxs, int n_ctx, const mg_region *regions, int n, int want, const mg_select_params *sp,

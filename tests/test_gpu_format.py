@@ -76,6 +76,20 @@ def test_device_records_equal_host_records(oracle):
         got = pnl.format_records(regions, np.array(idx_all), which, chrom="chr7_alt", first_index=first, middle=middle)
         assert len(idx_all) > 20000
         assert bytes(got) == want, "device-written records differ from print_details' bytes"
+        # the whole all_mips.txt in one call: K-replay finds the enumerated grid points on the device (with and without the
+        # logistic heuristic's early exits, mipgen.cpp:494)
+        for heuristic in (True, False):
+            if not heuristic:
+                idx_all, want = [], b""
+                for i, r in enumerate(regions):
+                    a, b = offs[i], offs[i + 1]
+                    enum_idx = mg.tile_replay(cfg, r, valid[a:b], score[a:b], method, False, upper)
+                    want += bytes(mg.design_records(cfg, r, enum_idx, score[a:b], "chr7_alt", r.label, r.start_flanked, r.stop_flanked,
+                                                    first + len(idx_all), middle=middle, raw=True))
+                    idx_all += list(enum_idx + a)
+            text, per_region = pnl.format_enumerated(regions, method, upper, heuristic=heuristic, chrom="chr7_alt", first_index=first, middle=middle)
+            assert int(per_region.sum()) == len(idx_all)
+            assert text == want, "device-enumerated all_mips.txt differs (method %d, heuristic %s)" % (method, heuristic)
     # regions with selection-only inputs are refused (their flags need design_mip)
     regions[0].snp = np.zeros(len(regions[0].seq), np.uint8)
     pnl2 = ctx.panel(regions)
