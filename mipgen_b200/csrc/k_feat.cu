@@ -381,6 +381,20 @@ k_feat_window(const DevConfig *__restrict__ cfg, const DevRegion *__restrict__ r
     for (int m = 0; m < 6; m++) { rowoff_f[m] = (int)((fd[m] >> 7) & 255) * stride; rowoff_r[m] = (int)((fd[m] >> 15) & 255) * stride; }
 
     const int max_arm = cfg->max_arm, min_arm = cfg->min_arm;
+    // row-table mode: prefix-table offsets and k-1 of the arm / insert ratio features, by (role, strand):
+    //   [0,84) arm table offsets [role][strand][21]; [84,126) arm k-1 [role][21]; [126,296) insert offsets [strand][85]; [296,381) insert k-1
+    __shared__ int rt_tab[384];
+    if (rows) {
+        for (int i = threadIdx.x; i < 381; i += blockDim.x) {
+            int f, strand = 0, want_km1 = 0;
+            if (i < 84) { const int role = i / 42, k = i % 21; strand = (i / 21) & 1; f = role ? 152 + k : k; }
+            else if (i < 126) { const int role = (i - 84) / 21, k = (i - 84) % 21; f = role ? 152 + k : k; want_km1 = 1; }
+            else if (i < 296) { strand = (i - 126) / 85; f = 66 + (i - 126) % 85; }
+            else { f = 66 + (i - 296); want_km1 = 1; }
+            const uint32_t d = fdesc[f];
+            rt_tab[i] = want_km1 ? (int)((d >> 5) & 3) : (int)((strand ? (d >> 15) : (d >> 7)) & 255) * stride;
+        }
+    }
 
     for (int ti = task0 + blockIdx.x; ti < task1; ti += gridDim.x) {
         const DevTask tk = tasks[ti];
@@ -593,100 +607,139 @@ k_feat_window(const DevConfig *__restrict__ cfg, const DevRegion *__restrict__ r
         //   rows [RA+RQ, R):     the insert [s, s + cap - sum - 1]
         // each as its block of the feature vector (21 ratios, length, log copy | 85 ratios, scan size) with -gamma ||row||^2
         // in the block's spare column -- exactly the tables k_svr_fact keeps in shared memory, so it fetches them with one bulk copy.
+        // One lane per row (32 rows per warp pass): the row's geometry is decoded once, its ratios come out of the prefix tables
+        // in a loop over the features, and the norm accumulates in the lane.
         if (rows) {
             const int fW = fc->W, n_ext = fc->n_ext, n_lig = fc->n_lig, n_sums = fc->n_sums, dsum = fc->max_sum - fc->min_sum;
-            const int n_sub = (tk.nsi + fW - 1) / fW;
-            const double kZeroNorm = -gamma * 0.0;
-            for (int ft = 0; ft < n_sub * tk.nci * 2; ft++) {
-                const int strand = ft & 1, cr = (ft >> 1) % tk.nci, sub = (ft >> 1) / tk.nci, ci = tk.ci0 + cr;
-                const int cap = wc.max_capture - ci * wc.inc;
+            const int n_pair = ((tk.nsi + fW - 1) / fW) * tk.nci;   // (sub-window, capture size) pairs of this task
+            const double kZeroNorm = -gamma * 0.0, kNegInf = __longlong_as_double(0xfff0000000000000LL);
+            auto r16 = [](int v) { return (v + 15) & ~15; };
+            // row counts of a full sub-window, per strand (a shorter last sub-window uses a prefix of each range)
+            const int capA0 = r16(fW * n_ext) + r16((fW + dsum) * n_lig), capA1 = r16(fW * n_lig) + r16((fW + dsum) * n_ext);
+            const int capI = r16(fW * n_sums);
+            struct Item { int ok, strand, ci, cap, nsi_f, s0; double *base; };
+            auto item_of = [&](int pair, int strand) {
+                Item it;
+                const int sub = pair / tk.nci, cr = pair - sub * tk.nci;
+                it.strand = strand; it.ci = tk.ci0 + cr; it.cap = wc.max_capture - it.ci * wc.inc;
                 // a capture size ruled out for the whole region (mipgen.cpp:429) scores nothing: k_svr_fact never fetches its tables
-                if (cap > r.stop_flanked - r.start_flanked + wc.max_mip_overlap && cap - wc.inc >= wc.min_capture) continue;
-                const int nsi_f = min(fW, tk.nsi - sub * fW);
+                it.ok = !(it.cap > r.stop_flanked - r.start_flanked + wc.max_mip_overlap && it.cap - wc.inc >= wc.min_capture);
+                it.nsi_f = min(fW, tk.nsi - sub * fW);
+                it.s0 = r.first_scan + tk.si0 + sub * fW;  // the work item's first scan start (chromosome coordinate)
+                it.base = rows + (int64_t)(tk.ft0 + (sub * wc.n_cap + it.ci) * 2 + strand - ftask_base) * fc->blob_doubles;
+                return it;
+            };
+            // the characters present: std::string::substr clamps the length (as candidate_geometry does); rows of scored
+            // candidates always lie inside the window's span, anything else is a dead row (zeros)
+            auto window_of = [&](bool live, int start, int len, int &a, int &n) {
+                const int off = start - r.seq_start;
+                live = live && len >= 0 && off >= 0 && off <= r.seq_len;
+                n = live ? min(len, r.seq_len - off) : 0;
+                a = off - span0;
+                return live && a >= 0 && a + n <= span_len;
+            };
+            auto ratio_of = [&](int tab_off, int km1, int a, int n, int len) {
+                const int end = a + n - km1;
+                const int cnt = (int)(uint16_t)(P[tab_off + max(end, a)] - P[tab_off + a]);
+                const int den = len - km1;
+                const double ad = (double)cnt, bd = (double)den;
+                if (den <= 0 || den >= kRecipN) return __ddiv_rn(ad, bd);
+                const double y = rn[den], q0 = __dmul_rn(ad, y);
+                return __fma_rn(__fma_rn(-q0, bd, ad), y, q0);
+            };
+            // ---- arm rows ----
+            const int n_arm = n_pair * (capA0 + capA1);
+            for (int i = warp * 32 + lane; i < n_arm; i += kWarpsPerBlock * 32) {
+                const int pair = i / (capA0 + capA1), rem = i - pair * (capA0 + capA1);
+                const int strand = rem >= capA0, row = rem - strand * capA0;
+                const Item it = item_of(pair, strand);
                 const int nA = strand ? n_lig : n_ext, nQ = strand ? n_ext : n_lig;
-                const int RA = (nsi_f * nA + 15) & ~15, RQ = ((nsi_f + dsum) * nQ + 15) & ~15, RI = (nsi_f * n_sums + 15) & ~15;
-                double *FAg = rows + (int64_t)(tk.ft0 + (sub * wc.n_cap + ci) * 2 + strand - ftask_base) * fc->blob_doubles;
-                double *FQg = FAg + fc->cap_FA, *FIg = FQg + fc->cap_FQ, *xxg = FIg + fc->cap_FI;
-                int *jcg = reinterpret_cast<int *>(xxg + fc->cap_R);
-                const int s0 = r.first_scan + tk.si0 + sub * fW;  // the work item's first scan start (chromosome coordinate)
-                for (int row = warp; row < RA + RQ + RI; row += kWarpsPerBlock) {
-                    int role, len = 0, start = 0;  // role 0 extension arm, 1 ligation arm, 2 insert
-                    bool live;
-                    double *dst;
-                    if (row < RA) {
-                        const int s_rel = row / nA, ia = row - s_rel * nA;
-                        live = s_rel < nsi_f; role = strand ? 1 : 0;
-                        len = strand ? fc->lig_of[ia] : fc->ext_of[ia];
-                        start = s0 + s_rel - len;
-                        dst = FAg + row * FACT_LD_ARM;
-                    } else if (row < RA + RQ) {
-                        const int m = row - RA, j = m / nQ, iq = m - j * nQ;
-                        live = j < nsi_f + dsum; role = strand ? 0 : 1;
-                        len = strand ? fc->ext_of[iq] : fc->lig_of[iq];
-                        start = s0 + j + cap - fc->max_sum;
-                        dst = FQg + m * FACT_LD_ARM;
-                    } else {
-                        const int m = row - RA - RQ, s_rel = m / n_sums, is = m - s_rel * n_sums;
-                        live = s_rel < nsi_f; role = 2;
-                        len = cap - fc->sum_of[is];  // scan size
-                        start = s0 + s_rel;
-                        dst = FIg + m * FACT_LD_INS;
-                    }
-                    // the characters present: std::string::substr clamps the length (as candidate_geometry does)
-                    const int off = start - r.seq_start;
-                    live = live && len >= 0 && off >= 0 && off <= r.seq_len;
-                    const int n = live ? min(len, r.seq_len - off) : 0, a = off - span0;
-                    live = live && a >= 0 && a + n <= span_len;   // rows of scored candidates always lie inside the window's span
-                    auto ratio_of = [&](int f) {
-                        const uint32_t d = fdesc[f];
-                        const int km1 = (d >> 5) & 3;
-                        const int prow = strand ? (int)((d >> 15) & 255) : (int)((d >> 7) & 255);
-                        const int end = a + n - km1;
-                        const int cnt = (int)(uint16_t)(P[prow * stride + max(end, a)] - P[prow * stride + a]);
-                        const int den = len - km1;
-                        const double ad = (double)cnt, bd = (double)den;
-                        if (den <= 0 || den >= kRecipN) return __ddiv_rn(ad, bd);
-                        const double y = rn[den], q0 = __dmul_rn(ad, y);
-                        return __fma_rn(__fma_rn(-q0, bd, ad), y, q0);
-                    };
-                    double v[3] = {0.0, 0.0, 0.0};
-                    int code = 16;
-                    if (live && role < 2) {
-                        if (lane < 21) v[0] = ratio_of(role ? 152 + lane : lane);
-                        else if (lane == 21) v[0] = (double)len;
-                        else if (lane == 22) v[0] = r.copy_off >= 0 ? log_copy(copy_lookup(cfg, r, copies, start, len), logtab) : 0.0;
-                        if (role == 1 && n >= 2) {
-                            const uint32_t j0 = strand ? codes_s[a + n - 1] : codes_s[a], j1 = strand ? codes_s[a + n - 2] : codes_s[a + 1];
-                            if (j0 < 4 && j1 < 4) code = strand ? (int)((3 - j0) * 4 + (3 - j1)) : (int)(j0 * 4 + j1);
-                        }
-                    } else if (live) {
-#pragma unroll
-                        for (int i = 0; i < 3; i++) {
-                            const int k = lane + 32 * i;
-                            if (k < 85) v[i] = ratio_of(66 + k);
-                            else if (k == 85) v[i] = (double)len;
-                        }
-                    }
-                    double ssum = 0.0;
-#pragma unroll
-                    for (int i = 0; i < 3; i++) ssum = fma(v[i], v[i], ssum);
-#pragma unroll
-                    for (int o = 16; o > 0; o >>= 1) ssum += __shfl_xor_sync(0xffffffffu, ssum, o);
-                    // a non-finite feature (log10(0) = -inf copy, a zero divisor) makes every kernel value of the row 0, as in libsvm:
-                    // the row is parked at exponent -inf with finite (zero) features so the contraction stays NaN free
-                    const bool finite = fabs(ssum) <= 1.7976931348623157e308;
-                    const double nrm = !live ? kZeroNorm : (finite ? -gamma * ssum : __longlong_as_double(0xfff0000000000000LL));
-                    if (role < 2) {
-                        if (lane < FACT_LD_ARM) dst[lane] = lane == FACT_K_ARM - 1 ? nrm : (finite ? v[0] : 0.0);
-                    } else {
-#pragma unroll
-                        for (int i = 0; i < 3; i++) {
-                            const int k = lane + 32 * i;
-                            if (k < FACT_LD_INS) dst[k] = k == FACT_K_INS - 2 ? nrm : (finite ? v[i] : 0.0);
-                        }
-                    }
-                    if (lane == 0) { xxg[row] = nrm; jcg[row] = role == 1 ? code : 16; }
+                const int RA = r16(it.nsi_f * nA), RQ = r16((it.nsi_f + dsum) * nQ);
+                if (!it.ok || row >= RA + RQ) continue;
+                int role, len, start;   // role 0 extension arm, 1 ligation arm
+                bool live;
+                double *dst;
+                if (row < RA) {
+                    const int s_rel = row / nA, ia = row - s_rel * nA;
+                    live = s_rel < it.nsi_f; role = strand ? 1 : 0;
+                    len = strand ? fc->lig_of[ia] : fc->ext_of[ia];
+                    start = it.s0 + s_rel - len;
+                    dst = it.base + row * FACT_LD_ARM;
+                } else {
+                    const int m = row - RA, j = m / nQ, iq = m - j * nQ;
+                    live = j < it.nsi_f + dsum; role = strand ? 0 : 1;
+                    len = strand ? fc->ext_of[iq] : fc->lig_of[iq];
+                    start = it.s0 + j + it.cap - fc->max_sum;
+                    dst = it.base + fc->cap_FA + m * FACT_LD_ARM;
                 }
+                int a, n;
+                live = window_of(live, start, len, a, n);
+                double ssum = 0.0;
+                int code = 16;
+                if (live) {
+                    const int *tab = rt_tab + (role * 2 + strand) * 21, *km = rt_tab + 84 + role * 21;
+#pragma unroll 3
+                    for (int k = 0; k < 21; k++) {
+                        const double v = ratio_of(tab[k], km[k], a, n, len);
+                        ssum = fma(v, v, ssum);
+                        dst[k] = v;
+                    }
+                    const double vl = (double)len, vc = r.copy_off >= 0 ? log_copy(copy_lookup(cfg, r, copies, start, len), logtab) : 0.0;
+                    ssum = fma(vl, vl, ssum);
+                    ssum = fma(vc, vc, ssum);
+                    dst[21] = vl; dst[22] = vc;
+                    if (role == 1 && n >= 2) {
+                        const uint32_t j0 = strand ? codes_s[a + n - 1] : codes_s[a], j1 = strand ? codes_s[a + n - 2] : codes_s[a + 1];
+                        if (j0 < 4 && j1 < 4) code = strand ? (int)((3 - j0) * 4 + (3 - j1)) : (int)(j0 * 4 + j1);
+                    }
+                }
+                // a non-finite feature (log10(0) = -inf copy, a zero divisor) makes every kernel value of the row 0, as in libsvm:
+                // the row is parked at exponent -inf with finite (zero) features so the contraction stays NaN free
+                const bool finite = fabs(ssum) <= 1.7976931348623157e308;
+                if (!live || !finite)
+                    for (int k = 0; k < FACT_K_ARM - 1; k++) dst[k] = 0.0;
+                const double nrm = !live ? kZeroNorm : (finite ? -gamma * ssum : kNegInf);
+                dst[FACT_K_ARM - 1] = nrm;
+                double *xxg = it.base + fc->cap_FA + fc->cap_FQ + fc->cap_FI;
+                xxg[row] = nrm;
+                reinterpret_cast<int *>(xxg + fc->cap_R)[row] = role == 1 ? code : 16;
+            }
+            // ---- insert rows ----
+            const int n_ins = n_pair * 2 * capI;
+            for (int i = warp * 32 + lane; i < n_ins; i += kWarpsPerBlock * 32) {
+                const int pair = i / (2 * capI), rem = i - pair * (2 * capI);
+                const int strand = rem >= capI, m = rem - strand * capI;
+                const Item it = item_of(pair, strand);
+                if (!it.ok || m >= r16(it.nsi_f * n_sums)) continue;
+                const int nA = strand ? n_lig : n_ext, nQ = strand ? n_ext : n_lig;
+                const int row = r16(it.nsi_f * nA) + r16((it.nsi_f + dsum) * nQ) + m;
+                const int s_rel = m / n_sums, is = m - s_rel * n_sums;
+                const int len = it.cap - fc->sum_of[is];  // scan size
+                double *dst = it.base + fc->cap_FA + fc->cap_FQ + m * FACT_LD_INS;
+                int a, n;
+                const bool live = window_of(s_rel < it.nsi_f, it.s0 + s_rel, len, a, n);
+                double ssum = 0.0;
+                if (live) {
+                    const int *tab = rt_tab + 126 + strand * 85, *km = rt_tab + 296;
+#pragma unroll 5
+                    for (int k = 0; k < 85; k++) {
+                        const double v = ratio_of(tab[k], km[k], a, n, len);
+                        ssum = fma(v, v, ssum);
+                        dst[k] = v;
+                    }
+                    const double vl = (double)len;
+                    ssum = fma(vl, vl, ssum);
+                    dst[85] = vl;
+                }
+                const bool finite = fabs(ssum) <= 1.7976931348623157e308;
+                if (!live || !finite)
+                    for (int k = 0; k < FACT_K_INS - 2; k++) dst[k] = 0.0;
+                const double nrm = !live ? kZeroNorm : (finite ? -gamma * ssum : kNegInf);
+                dst[FACT_K_INS - 2] = nrm;
+                dst[FACT_K_INS - 1] = 0.0;
+                double *xxg = it.base + fc->cap_FA + fc->cap_FQ + fc->cap_FI;
+                xxg[row] = nrm;
+                reinterpret_cast<int *>(xxg + fc->cap_R)[row] = 16;
             }
         }
     }
