@@ -94,6 +94,21 @@ __device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t da, uint64_t 
         "l"(da), "l"(db), "r"(idesc), "r"(accumulate)
         : "memory");
 }
+// the same with the A operand in tensor memory (lane = row, two FP16 per 32-bit column: 8 columns per K = 16 step)
+__device__ __forceinline__ void umma_f16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t db, uint32_t idesc, uint32_t accumulate)
+{
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}\n" ::"r"(tmem_d),
+        "r"(tmem_a), "l"(db), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// shared memory -> tensor memory: 128 rows x 32 bytes (one K = 16 step of a K-major FP16 operand) into 8 columns; ordered with
+// the tcgen05.mma instructions the same thread issues afterwards (tools/probe_tmem_a.cu checks both)
+__device__ __forceinline__ void tmem_cp_128x256b(uint32_t taddr, uint64_t sdesc)
+{
+    asm volatile("tcgen05.cp.cta_group::1.128x256b [%0], %1;" ::"r"(taddr), "l"(sdesc) : "memory");
+}
 __device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t (&v)[8])
 {
     asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
@@ -152,6 +167,12 @@ __device__ __forceinline__ void expn(double (&t)[N], uint32_t tab256)
 // 32 no operand-image copies
 #ifndef MG_TC_ABLATE
 #define MG_TC_ABLATE 0
+#endif
+// 1: the FP16 hi / lo tiles of the A operand are staged once per CTA from shared into tensor memory (columns 384..511, next to
+// the 2 x 192 accumulator columns) and the 24 fractional MMAs of every SV tile read them there: the tensor core then takes
+// 2 KB instead of 6 KB per MMA out of shared memory, which the FP64 epilogue's look-ups share
+#ifndef MG_TC_A_TMEM
+#define MG_TC_A_TMEM 1
 #endif
 
 // -DMG_TC_TRACE: CTA 1000 of a launch writes clock64 timestamps of its pipeline events to a global buffer (tools/trace_tc.py)
@@ -313,6 +334,15 @@ k_svr_tc(const DevRegion *__restrict__ regions, const int64_t *__restrict__ tile
             // D = F32, A = B = F16, both K-major, N >> 3 at [17,23), M >> 4 at [24,29)
             const uint32_t idesc = (1u << 4) | ((uint32_t)(TC_N >> 3) << 17) | ((uint32_t)(TC_M >> 4) << 24);
             const uint32_t a_hi = smem_u32(smem + kOffAhi), a_lo = smem_u32(smem + kOffAlo), a_i = smem_u32(smem + kOffAI);
+            const uint32_t ta_hi = tmem_d + 384, ta_lo = tmem_d + 448;
+            if (MG_TC_A_TMEM) {
+#pragma unroll
+                for (int ks = 0; ks < TC_KF / 16; ks++) {
+                    const uint32_t ao = (uint32_t)(ks >> 2) * (TC_M * 128) + (uint32_t)(ks & 3) * 32;
+                    tmem_cp_128x256b(ta_hi + ks * 8, umma_desc(a_hi + ao));
+                    tmem_cp_128x256b(ta_lo + ks * 8, umma_desc(a_lo + ao));
+                }
+            }
             for (int j = 0; j < n_tiles; j++) {
                 const int s = j % TC_STAGES, ds = j & 1;
                 mbar_wait(&b_full[s], (j / TC_STAGES) & 1);
@@ -327,9 +357,15 @@ k_svr_tc(const DevRegion *__restrict__ regions, const int64_t *__restrict__ tile
 #pragma unroll
                     for (int ks = 0; ks < TC_KF / 16; ks++) {  // K block of 64 columns = one 128-byte swizzle row; 4 steps of 32 bytes inside
                         const uint32_t ao = (uint32_t)(ks >> 2) * (TC_M * 128) + (uint32_t)(ks & 3) * 32, bo = (uint32_t)(ks >> 2) * (TC_N * 128) + (uint32_t)(ks & 3) * 32;
-                        umma_f16(d_hh, umma_desc(a_hi + ao), umma_desc(b_hi + bo), idesc, ks > 0);
-                        umma_f16(d_x, umma_desc(a_hi + ao), umma_desc(b_lo + bo), idesc, ks > 0);
-                        umma_f16(d_x, umma_desc(a_lo + ao), umma_desc(b_hi + bo), idesc, 1);
+                        if (MG_TC_A_TMEM) {
+                            umma_f16_ts(d_hh, ta_hi + ks * 8, umma_desc(b_hi + bo), idesc, ks > 0);
+                            umma_f16_ts(d_x, ta_hi + ks * 8, umma_desc(b_lo + bo), idesc, ks > 0);
+                            umma_f16_ts(d_x, ta_lo + ks * 8, umma_desc(b_hi + bo), idesc, 1);
+                        } else {
+                            umma_f16(d_hh, umma_desc(a_hi + ao), umma_desc(b_hi + bo), idesc, ks > 0);
+                            umma_f16(d_x, umma_desc(a_hi + ao), umma_desc(b_lo + bo), idesc, ks > 0);
+                            umma_f16(d_x, umma_desc(a_lo + ao), umma_desc(b_hi + bo), idesc, 1);
+                        }
                         if (ks < 2) umma_f16(d_i, umma_desc(a_i + ks * 32), umma_desc(b_i + ks * 32), idesc, ks > 0);  // 19 integer columns, padded to 32
                     }
                 }
