@@ -347,6 +347,27 @@ int mg_partition_regions(const mg_config *cfg, const mg_region *regions, int n, 
 /* scores of n grid points of a scored panel (panel-global indices; -1 yields NaN); logistic / svr may be NULL */
 int mg_panel_gather(mg_ctx *ctx, mg_panel *p, const int64_t *idx, int64_t n, double *logistic, double *svr);
 
+/* ---- SURVEY.md 8(f4), OPT-IN: exact-match arm copy counting on the device -------------------------------------------------------
+ * Replaces `bwa aln` + `bwa samse` on <project>.oligo_copy_count.fq and find_copy's parse of the X0 tag (mipgen.cpp:558-596, reads
+ * written at 824-836) for what X0 is on reads cut out of the indexed genome: the number of EXACT occurrences of the oligo on either
+ * strand.  Nothing in the library calls it by itself: it changes the contract of an external tool (BWA also reports hits with
+ * mismatches when a read has no exact hit), so a caller opts in by filling mg_region.copies from it (route C).
+ *
+ * mg_genome_create   index of the given contigs (plain sequences, any case; every character other than ACGT separates): the sorted
+ *                    2-bit packed 32-mers of all positions, resident in HBM (8 bytes per base).
+ * mg_count_arm_copies  for every region and oligo size (1..32 bases) a table in the layout of mg_region.copies, [n_oligo_sizes][seq_len]:
+ *                    entry (k, i) = occurrences of seq[i .. i + size_k - 1] plus occurrences of its reverse complement, as find_copy
+ *                    stores X0; 100 (find_copy's value for a read without X0) when the oligo holds a character other than ACGT or
+ *                    does not occur in the index; 0 = absent key for the starts the reference never writes (i >= seq_len - size_k,
+ *                    mipgen.cpp:829).  copies_off[n + 1] (may be NULL) receives each region's offset in `copies`; with
+ *                    copies == NULL only the offsets are computed. */
+typedef struct mg_genome mg_genome;
+int mg_genome_create(mg_ctx *ctx, const char *const *seqs, const int64_t *lens, int n_contigs, mg_genome **out);
+void mg_genome_destroy(mg_genome *g);
+int mg_genome_info(const mg_genome *g, int64_t *positions, int64_t *indexed, int64_t *short_suffixes);
+int mg_count_arm_copies(mg_genome *g, const mg_region *regions, int n, const int *oligo_sizes, int n_oligo_sizes, int32_t *copies,
+                        int64_t *copies_off);
+
 #ifdef __cplusplus
 }
 #endif

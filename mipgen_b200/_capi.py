@@ -129,6 +129,10 @@ SYMBOLS = [
                                          c_ubyte_p, c_double_p, c_double_p]),
     ("mg_partition_regions", C.c_int, [C.POINTER(MgConfig), C.POINTER(MgRegion), C.c_int, C.c_int, c_int_p]),
     ("mg_panel_gather", C.c_int, [C.c_void_p, C.c_void_p, c_int64_p, C.c_int64, c_double_p, c_double_p]),
+    ("mg_genome_create", C.c_int, [C.c_void_p, C.POINTER(C.c_char_p), c_int64_p, C.c_int, C.POINTER(C.c_void_p)]),
+    ("mg_genome_destroy", None, [C.c_void_p]),
+    ("mg_genome_info", C.c_int, [C.c_void_p, c_int64_p, c_int64_p, c_int64_p]),
+    ("mg_count_arm_copies", C.c_int, [C.c_void_p, C.POINTER(MgRegion), C.c_int, c_int_p, C.c_int, c_int_p, c_int64_p]),
     ("mg_panel_format_records", C.c_int64, [C.c_void_p, C.c_void_p, C.POINTER(MgRecordMeta), c_int64_p, C.c_int64, C.c_int, C.c_char_p,
                                             C.c_int, C.c_void_p, C.c_int64]),
     ("mg_panel_format_enumerated", C.c_int64, [C.c_void_p, C.c_void_p, C.POINTER(MgRecordMeta), C.POINTER(MgSelectParams), C.c_char_p, C.c_int,
@@ -630,6 +634,10 @@ class Context:
                                               _ptr(lo, c_double_p), _ptr(sv, c_double_p), _ptr(ft, c_double_p)))
         return offsets, valid, lo, sv, ft
 
+    def genome(self, contigs: Sequence[str]) -> "Genome":
+        """Exact-match index of the given contig sequences, resident on the device (mg_genome_create; SURVEY.md 8 f4, opt-in)."""
+        return Genome(self, contigs)
+
     def panel(self, regions: Sequence[Region]) -> Panel:
         arr, keep = self._regions(regions)
         n = len(regions)
@@ -639,3 +647,45 @@ class Context:
         h = C.c_void_p()
         self._check(self.lib.mg_panel_create(self.h, arr, n, C.byref(h)))
         return Panel(self, h, offsets, keep)
+
+
+class Genome:
+    """mg_genome: sorted 32-mers of a reference genome in HBM; counts exact occurrences of arm-sized oligos on both strands."""
+
+    def __init__(self, ctx: Context, contigs: Sequence[str]):
+        self.ctx = ctx
+        raw = [c.encode() if isinstance(c, str) else bytes(c) for c in contigs]
+        n = len(raw)
+        seqs = (C.c_char_p * max(n, 1))(*raw)
+        lens = np.asarray([len(b) for b in raw], np.int64)
+        h = C.c_void_p()
+        ctx._check(ctx.lib.mg_genome_create(ctx.h, seqs, _ptr(lens, c_int64_p), n, C.byref(h)))
+        self.h = h
+
+    def info(self):
+        """(positions, positions with 32 valid bases ahead, short suffixes)"""
+        a, b, c = (np.zeros(1, np.int64) for _ in range(3))
+        self.ctx.lib.mg_genome_info(self.h, _ptr(a, c_int64_p), _ptr(b, c_int64_p), _ptr(c, c_int64_p))
+        return int(a[0]), int(b[0]), int(c[0])
+
+    def count_arm_copies(self, regions: Sequence[Region], oligo_sizes: Sequence[int]):
+        """One int32 table [n_oligo_sizes][seq_len] per region, in the layout of Region.copies (mg_count_arm_copies)."""
+        arr, _keep = _c_regions(regions)
+        n = len(regions)
+        sizes = np.asarray(list(oligo_sizes), np.int32)
+        off = np.zeros(n + 1, np.int64)
+        self.ctx._check(self.ctx.lib.mg_count_arm_copies(self.h, arr, n, _ptr(sizes, c_int_p), sizes.size, c_int_p(), _ptr(off, c_int64_p)))
+        flat = np.zeros(max(int(off[-1]), 1), np.int32)
+        self.ctx._check(self.ctx.lib.mg_count_arm_copies(self.h, arr, n, _ptr(sizes, c_int_p), sizes.size, _ptr(flat, c_int_p), _ptr(off, c_int64_p)))
+        return [flat[off[i]:off[i + 1]].reshape(sizes.size, len(regions[i].seq)) for i in range(n)]
+
+    def close(self):
+        if self.h:
+            self.ctx.lib.mg_genome_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
