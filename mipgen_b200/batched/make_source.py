@@ -4,14 +4,16 @@
     python make_source.py /root/reference/mipgen.cpp _build/mipgen_batched.cpp
 
 Reads the reference's mipgen.cpp WHERE IT LIES and writes a patched copy into the (git-ignored) build directory; nothing
-of the reference is stored in this repository.  Four anchored edits, each checked to match exactly once:
+of the reference is stored in this repository.  Five anchored edits, each checked to match exactly once:
 
   1. `#include "mipgen_batched.h"` before `class mipgen{`, `#include "batched_members.inc"` right after its `public:`;
   2. tile_regions (mipgen.cpp:403-556): the statements from the initialisation of current_scan_start_position (:421)
      through `collapse_mips();` (:505) become `b200_tile_feature(feature);`;
   3. predict_value (mipgen.cpp:1948): first statement returns the device score parked by get_parameters, if any;
   4. check_copy_numbers (mipgen.cpp:796-873): the loops that print all_sequences.fq / oligo_copy_count.fq (:804-838) become
-     `b200_write_fastqs(BWAFQ, ARMSFQ);` (the bwa calls and the SAM parsing that follow are untouched).
+     `b200_write_fastqs(BWAFQ, ARMSFQ);` (the bwa calls and the SAM parsing that follow are untouched);
+  5. find_copy (mipgen.cpp:558-596): first statement `if (b200_find_copy()) return;` -- a no-op unless the user opts in to exact-match
+     arm copy counting on the device with MIPGEN_B200_EXACT_COPIES.
 """
 import re
 import sys
@@ -47,6 +49,9 @@ def main():
     if not (a.start() < b.start()):
         sys.exit("make_source.py: FASTQ anchors out of order")
     t = t[:a.start()] + "\tb200_write_fastqs(BWAFQ, ARMSFQ); // mipgen_b200: both FASTQ files formatted on the GPU\n" + t[b.start():]
+    # 5. find_copy: opt-in replacement of the bwa run on oligo_copy_count.fq
+    m = one(r"void\s+find_copy\s*\(\s*\)\s*\{", t, "find_copy")
+    t = t[:m.end()] + "\n\tif (b200_find_copy()) return; // mipgen_b200: exact-match copy counting on the GPU when MIPGEN_B200_EXACT_COPIES is set\n" + t[m.end():]
     open(dst, "w", encoding="latin-1", newline="").write(t)
 
 

@@ -12,14 +12,18 @@
 #   capture reads  "<size>_<c>_<start>"      X0 = 2 when (start + size) % 53 == 0 (ambiguous site)
 # MIPGEN_STUB_RULES=2: the arm rule only (no ambiguous sites: design_mip leaves masking_failed uninitialised after a
 # mapping failure, mipgen.cpp:622-624, so all_mips.txt of such a run is not reproducible even by the reference itself)
+# MIPGEN_STUB_RULES=3: arm reads take X0 from the two-column file MIPGEN_STUB_X0_FILE (read name, X0; absent names get 1) -- used to
+# replay exact-match copy counts (tests/test_copy_count.py) through the reference's own find_copy
 [ $# -eq 0 ] && exit 1
 case "$1" in
   aln) exit 0 ;;
   samse)
-    awk -v rules="${MIPGEN_STUB_RULES:-0}" '
+    awk -v rules="${MIPGEN_STUB_RULES:-0}" -v x0file="${MIPGEN_STUB_X0_FILE:-}" '
+      BEGIN { if (rules == 3 && x0file != "") while ((getline line < x0file) > 0) { split(line, f, "\t"); tab[f[1]] = f[2] } }
       NR%4==1 { n = substr($0, 2) }
       NR%4==2 {
         x0 = 1
+        if (rules == 3 && (n in tab)) x0 = tab[n] + 0
         if (rules == 1 || rules == 2) {
           if (n ~ /^chr/) {
             split(n, a, ":"); split(a[2], b, "-"); start = b[1] + 0; stop = b[2] + 0

@@ -134,3 +134,57 @@ def test_copy_tables_feed_the_scorer(tmp_path):
     assert rel_err(sv, np.concatenate([w[2] for w in want])) <= 1e-9
     g.close()
     ctx.close()
+
+
+@pytest.mark.gpu
+def test_batched_cli_with_exact_copies_equals_reference_fed_the_same_x0(tmp_path):
+    """Route C with MIPGEN_B200_EXACT_COPIES=1 (find_copy answered by mg_count_arm_copies, no bwa run on the oligo reads) against the
+    unmodified reference CLI whose stub bwa replays, read by read, the exact-match counts of the brute-force restatement as X0
+    tags: every design file byte-identical.  The genome holds a direct and an inverted copy of a stretch of one region, so arms
+    with copy 2 and 3 exist and move the logistic scores (SVMipv4.cpp:173-174)."""
+    import filecmp
+    from cli_util import run_cli, REF_CLI
+    batched = os.path.join(ROOT, "mipgen_b200", "dropin", "_build", "mipgen_batched")
+    if not (os.path.exists(REF_CLI) and os.path.exists(batched)):
+        pytest.skip("reference / batched CLI not prebuilt (needs /root/reference at build time)")
+    d = str(tmp_path)
+    cfg = panel.Config(162, 157, 5)
+    genome = bytearray(panel.lcg_genome(60000, 4242))
+    regs = panel.make_regions(bytes(genome), 2, 120, 170, cfg, 4243)
+    src = regs[0].start_flanked - 1
+    genome[400:480] = genome[src:src + 80]
+    genome[700:760] = cc.revcomp(bytes(genome[src + 20:src + 80]))
+    genome = bytes(genome)
+    gdir = os.path.join(d, "genome")
+    os.makedirs(gdir)
+    panel.write_fasta(os.path.join(gdir, "chr1.fa"), "chr1", genome)
+    bed = os.path.join(d, "r.bed")
+    panel.write_bed(bed, regs)
+    flags = ["-min_capture_size", "157", "-max_capture_size", "162", "-arm_length_sums", "40,45", "-logistic_optimal_score", "0.9",
+             "-logistic_priority_score", "0.8"]
+    # 1. the reads the CLI asks BWA about
+    probe, _ = run_cli(REF_CLI, d, "probe", bed, gdir, flags)
+    lines = open(os.path.join(probe, "p.oligo_copy_count.fq")).read().split("\n")
+    names, seqs = lines[0::4], lines[1::4]
+    tables = {}
+    x0 = os.path.join(d, "x0.tsv")
+    n_multi = 0
+    with open(x0, "w") as f:
+        for name, s in zip(names, seqs):
+            if not name:
+                continue
+            q = s.encode()
+            if len(q) not in tables:
+                tables[len(q)] = cc.kmer_table([genome], len(q))
+            tab = tables[len(q)]
+            n = tab.get(q, 0) + tab.get(cc.revcomp(q), 0)
+            n_multi += n > 1
+            f.write("%s\t%d\n" % (name[1:], n))
+    assert n_multi > 50
+    # 2. the reference with those X0 tags, the batched driver counting on the device (its stub bwa would say 1 everywhere)
+    ref_dir, _ = run_cli(REF_CLI, d, "ref", bed, gdir, flags, env_extra={"MIPGEN_STUB_RULES": "3", "MIPGEN_STUB_X0_FILE": x0})
+    new_dir, log = run_cli(batched, d, "b200", bed, gdir, flags, env_extra={"MIPGEN_B200_EXACT_COPIES": "1"})
+    for name in ("p.all_mips.txt", "p.collapsed_mips.txt", "p.picked_mips.txt"):
+        assert filecmp.cmp(os.path.join(ref_dir, name), os.path.join(new_dir, name), shallow=False), name + " differs"
+    # the copies did matter: a run with copy 1 everywhere scores differently
+    assert not filecmp.cmp(os.path.join(probe, "p.all_mips.txt"), os.path.join(ref_dir, "p.all_mips.txt"), shallow=False)
