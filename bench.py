@@ -595,6 +595,23 @@ def extra_blocks(ctx, cfg, work, args):
                           "scan_start_winners": int((t.scan_best >= 0).sum()),
                           "extrapolation": "the full config (2e5 regions, ~6e9 candidates) is 10x this work: ~%.0f s on one GPU, ~%.0f s on 8 "
                                            "(regions shard without exchange)" % (dt * 10, dt * 10 / 8)}
+    # SURVEY 8(f4), opt-in: exact-match arm copy counting against an index of the cfg5 genome (what find_copy gets from BWA's X0 tags)
+    t0 = time.perf_counter()
+    gen = ctx.genome([g5.decode()])
+    t_index = time.perf_counter() - t0
+    sub = r5[:4000]
+    gen.count_arm_copies(sub[:50], cfg.oligo_sizes)
+    t0 = time.perf_counter()
+    tabs = gen.count_arm_copies(sub, cfg.oligo_sizes)
+    t_query = time.perf_counter() - t0
+    n_oligos = int(sum(t.size for t in tabs))
+    out["copy_count"] = {"what": "opt-in replacement of `bwa aln/samse` on oligo_copy_count.fq (mipgen.cpp:558-596): exact occurrences on both strands of "
+                                 "every arm-sized oligo (%d sizes) of %d regions in a %.1f Mb genome, through mg_genome_create / mg_count_arm_copies "
+                                 "(host buffers in, copy tables out)" % (len(cfg.oligo_sizes), len(sub), len(g5) / 1e6),
+                         "index_seconds": t_index, "indexed_positions": gen.info()[1], "oligos": n_oligos, "query_seconds": t_query,
+                         "value": n_oligos / t_query, "unit": "oligos/s (end to end)",
+                         "multi_copy_fraction": float(np.mean(np.concatenate([(t > 1).ravel() for t in tabs[:200]])))}
+    gen.close()
     return out
 
 
