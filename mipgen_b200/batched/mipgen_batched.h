@@ -1,13 +1,16 @@
 // mipgen_batched.h -- file-scope declarations for the batched MIPgen driver (INTEGRATION.md route C).
 //
-// The batched driver is the reference's own mipgen.cpp with four anchored edits applied at BUILD time by
+// The batched driver is the reference's own mipgen.cpp with five anchored edits applied at BUILD time by
 // make_source.py (no reference code lives in this repository):
 //   1. this header is included before `class mipgen`, and batched_members.inc inside it;
 //   2. in tile_regions (mipgen.cpp:403-556) the per-feature candidate loop nest + condense_mips + collapse_mips
 //      (mipgen.cpp:421-505) is replaced by one call, b200_tile_feature(feature), which takes the winners of a whole
 //      batch of features from mg_tile_regions_multi and materialises SVMipv4 objects only for them;
 //   3. predict_value (mipgen.cpp:1948-2019) returns the device's SVR score of the object get_parameters was just
-//      called on, instead of printing and re-parsing its 192 features.
+//      called on, instead of printing and re-parsing its 192 features;
+//   4. check_copy_numbers' FASTQ loops (mipgen.cpp:804-838) become one device call, b200_write_fastqs;
+//   5. find_copy (mipgen.cpp:558-596) starts with `if (b200_find_copy()) return;`: a no-op unless MIPGEN_B200_EXACT_COPIES switches the
+//      opt-in exact-match arm copy counting on.
 // Everything else -- flag parsing, BED / FASTA / BWA / TRF / tabix handling, design_mip, pick_mips and its helpers,
 // print_details and the output files -- is the reference's code, compiled unchanged.
 #ifndef MIPGEN_B200_BATCHED_H
