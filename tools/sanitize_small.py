@@ -2,7 +2,8 @@
 """A small tour of every kernel for compute-sanitizer (memcheck / racecheck / initcheck):
     compute-sanitizer --tool memcheck python tools/sanitize_small.py
 Two configs through one context (narrow -> wide arm table), SVR in all three forms, logistic, features, select with selection inputs,
-device-written records and all_mips.txt, FASTQ writers, mg_tile_regions."""
+device-written records and all_mips.txt, FASTQ writers, mg_tile_regions, and the opt-in exact-match copy counting (genome index with
+N runs, lower case and a contig shorter than 32 bases)."""
 import os
 import sys
 
@@ -44,6 +45,14 @@ def main():
         assert (t.scan_best >= -1).all()
         ctx.fastq(regions, "1", oligo=False)
         ctx.fastq(regions, "1", oligo=True)
+    g = bytearray(panel.lcg_genome(20000, 3))
+    g[5000:5040] = b"N" * 40
+    g[9000:9100] = bytes(g[9000:9100]).lower()
+    gen = ctx.genome([bytes(g).decode(), "ACGTTGCAAGGCTTAACCGGTTAA", ""])
+    regions[0].copies = None
+    tabs = gen.count_arm_copies(regions + [panel.Region(10, 20, 1, 30, bytes(g[4990:5020]))], [16, 24, 32, 1])
+    assert all(t.min() >= 0 for t in tabs)
+    gen.close()
     ctx.close()
     print("sanitize tour done")
 
