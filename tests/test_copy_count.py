@@ -188,3 +188,17 @@ def test_batched_cli_with_exact_copies_equals_reference_fed_the_same_x0(tmp_path
         assert filecmp.cmp(os.path.join(ref_dir, name), os.path.join(new_dir, name), shallow=False), name + " differs"
     # the copies did matter: a run with copy 1 everywhere scores differently
     assert not filecmp.cmp(os.path.join(probe, "p.all_mips.txt"), os.path.join(ref_dir, "p.all_mips.txt"), shallow=False)
+
+
+def test_stub_bwa_replays_x0_tags_from_a_file(tmp_path):
+    """oracle/stub_bwa.sh, MIPGEN_STUB_RULES=3: the X0 tag of an arm read comes from MIPGEN_STUB_X0_FILE, anything else stays 1."""
+    import subprocess
+    fq = tmp_path / "r.fq"
+    fq.write_text("@chr1:100-115\nACGTACGTACGTACGT\n+\n################\n@chr1:101-116\nCGTACGTACGTACGTA\n+\n################\n")
+    x0 = tmp_path / "x0.tsv"
+    x0.write_text("chr1:100-115\t7\n")
+    env = dict(os.environ, MIPGEN_STUB_RULES="3", MIPGEN_STUB_X0_FILE=str(x0))
+    out = subprocess.run(["bash", os.path.join(ROOT, "oracle", "stub_bwa.sh"), "samse", "idx", "sai", str(fq)], env=env, capture_output=True, text=True)
+    assert out.returncode == 0
+    lines = out.stdout.strip().split("\n")
+    assert len(lines) == 2 and lines[0].startswith("chr1:100-115\t") and "X0:i:7\t" in lines[0] and "X0:i:1\t" in lines[1]
