@@ -7,6 +7,7 @@ from __future__ import annotations
 
 import ctypes as C
 import os
+import time
 from typing import List, Optional, Sequence
 
 import numpy as np
@@ -259,6 +260,7 @@ def tile_regions(ctxs, regions: Sequence[Region], want: int, select=None, full_g
                             select.get("max_arm_copy", 75), select.get("target_arm_copy", 20), select.get("masked_arm_threshold", 0.5))
     spp = C.byref(sp) if sp is not None else None
     lib = first.lib
+    t0 = time.perf_counter()
     if multi:
         hs = (C.c_void_p * len(ctxs))(*[c.h for c in ctxs])
         rc = lib.mg_tile_regions_multi(hs, len(ctxs), arr, len(regions), want, spp, max_batch_candidates, C.byref(res))
@@ -266,7 +268,9 @@ def tile_regions(ctxs, regions: Sequence[Region], want: int, select=None, full_g
             raise MgError("mg_tile_regions_multi failed (%d): %s" % (rc, "; ".join(lib.mg_last_error(c.h).decode() for c in ctxs)))
     else:
         first._check(lib.mg_tile_regions(first.h, arr, len(regions), want, spp, max_batch_candidates, C.byref(res)))
-    return TileResult(g, s, p, sb, pb, sbl, sbs, v, lo, sv)
+    out = TileResult(g, s, p, sb, pb, sbl, sbs, v, lo, sv)
+    out.call_seconds = time.perf_counter() - t0   # the C call alone (the ctypes marshalling of the regions above is the wrapper's)
+    return out
 
 
 def config_grid_size(cfg: Config, r: Region) -> int:
