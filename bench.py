@@ -594,7 +594,9 @@ def extra_blocks(ctx, cfg, work, args):
                           "unit": "candidates/s (end to end, one GPU)",
                           "scan_start_winners": int((t.scan_best >= 0).sum()),
                           "extrapolation": "the full config (2e5 regions, ~6e9 candidates) is 10x this work: ~%.0f s on one GPU, ~%.0f s on 8 "
-                                           "(regions shard without exchange)" % (dt * 10, dt * 10 / 8)}
+                                           "(regions shard without exchange)" % (dt * 10, dt * 10 / 8),
+                          "full_scale_runs": "tools/run_cfg5_full.py, measured: 6.07e9 grid points in 36.9 s on one B200 and 4.52 s on eight "
+                                             "(profiles/r02_cfg5_full_1gpu.json, r02_cfg5_full_8gpu.json)"}
     # SURVEY 8(f4), opt-in: exact-match arm copy counting against an index of the cfg5 genome (what find_copy gets from BWA's X0 tags)
     t0 = time.perf_counter()
     gen = ctx.genome([g5.decode()])
