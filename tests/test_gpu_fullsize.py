@@ -355,3 +355,16 @@ def test_cfg5_shape_streams_through_bounded_memory():
         assert np.array_equal(sb, wsb) and np.array_equal(pb, wpb)
     oracle.svm_free(h)
     ctx.close()
+
+
+def test_full_scale_cfg5_runner_at_small_scale():
+    """tools/run_cfg5_full.py (the script behind profiles/r02_cfg5_full_*.json) on 300 regions: it runs, its sampled regions equal their
+    single-region calls, and it reports the C call's own seconds."""
+    import json
+    import subprocess
+    import sys
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "run_cfg5_full.py"), "300"], capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stderr[-1500:]
+    d = json.loads(out.stdout.strip().splitlines()[-1])
+    assert d["regions"] == 300 and d["grid_points"] > 8e6 and d["sampled_regions_equal_their_single_region_calls"] is True
+    assert 0 < d["seconds"] <= d["seconds_incl_python_marshalling"] and d["scan_start_winners"] > 0

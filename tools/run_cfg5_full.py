@@ -60,7 +60,7 @@ def main():
     n_grid = int(t.grid_off[-1])
     # consistency: a sample of regions on their own
     rng = np.random.default_rng(1)
-    pick = sorted(rng.choice(n, 40, replace=False).tolist())
+    pick = sorted(rng.choice(n, min(40, n), replace=False).tolist())
     same = True
     for i in pick:
         one = mg.tile_regions(ctxs[0], [regions[i]], mg.MG_WANT_SVR, select=sel)
