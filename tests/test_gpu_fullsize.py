@@ -363,7 +363,8 @@ def test_full_scale_cfg5_runner_at_small_scale():
     import json
     import subprocess
     import sys
-    out = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "run_cfg5_full.py"), "300"], capture_output=True, text=True, timeout=600)
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, os.path.join(root, "tools", "run_cfg5_full.py"), "300"], capture_output=True, text=True, timeout=600)
     assert out.returncode == 0, out.stderr[-1500:]
     d = json.loads(out.stdout.strip().splitlines()[-1])
     assert d["regions"] == 300 and d["grid_points"] > 8e6 and d["sampled_regions_equal_their_single_region_calls"] is True
