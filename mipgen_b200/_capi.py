@@ -642,6 +642,23 @@ class Context:
         """Exact-match index of the given contig sequences, resident on the device (mg_genome_create; SURVEY.md 8 f4, opt-in)."""
         return Genome(self, contigs)
 
+    def prepare_regions(self, regions: Sequence[Region]):
+        """The mg_region array of `regions` and their grid offsets, built once: what a C caller holds before it calls
+        mg_score_regions (the ctypes marshalling costs ~12 us per region and is the wrapper's, not the library's)."""
+        arr, keep = self._regions(regions)
+        n = len(regions)
+        offsets = np.zeros(n + 1, np.int64)
+        for i in range(n):
+            offsets[i + 1] = offsets[i] + self.lib.mg_grid_size(self.h, C.byref(arr[i]))
+        return arr, keep, n, offsets
+
+    def score_regions_prepared(self, prep, want: int, out):
+        """mg_score_regions on a prepared mg_region array (H2D + kernels + D2H inside); out = (valid, logistic, svr, features) buffers."""
+        arr, _keep, n, offsets = prep
+        valid, lo, sv, ft = out
+        self._check(self.lib.mg_score_regions(self.h, arr, n, want, _ptr(offsets, c_int64_p), _ptr(valid, c_ubyte_p),
+                                              _ptr(lo, c_double_p), _ptr(sv, c_double_p), _ptr(ft, c_double_p)))
+
     def panel(self, regions: Sequence[Region]) -> Panel:
         arr, keep = self._regions(regions)
         n = len(regions)
