@@ -585,13 +585,13 @@ def extra_blocks(ctx, cfg, work, args):
     for _ in range(2):   # the first pass also grows the context's workspaces to the size of a full sub-batch
         t0 = time.perf_counter()
         t = mg.tile_regions(ctx, r5, mg.MG_WANT_SVR, select=sel)
-        passes.append(time.perf_counter() - t0)
-    dt = passes[-1]
+        passes.append((t.call_seconds, time.perf_counter() - t0))
+    dt, dt_py = passes[-1]   # the C call itself; with the Python wrapper's ctypes marshalling of the region structs
     n_grid = int(t.grid_off[-1])
     out["cfg5_sample"] = {"what": "BASELINE configs[4] shape at 1/10 scale: %d regions of U[100,200] bp (%.1f Mb of targets), capture 162, SVR, through "
                                   "mg_tile_regions in sub-batches of <= 2^26 grid points (bounded device memory; host buffers in, winners out)"
                                   % (n5, sum(r.stop_flanked - r.start_flanked + 1 for r in r5) / 1e6),
-                          "grid_points": n_grid, "seconds": dt, "seconds_first_pass": passes[0], "value": n_grid / dt,
+                          "grid_points": n_grid, "seconds": dt, "seconds_incl_python_marshalling": dt_py, "seconds_first_pass": passes[0][0], "value": n_grid / dt,
                           "unit": "candidates/s (end to end, one GPU)",
                           "scan_start_winners": int((t.scan_best >= 0).sum()),
                           "extrapolation": "the full config (2e5 regions, ~6e9 candidates) is 10x this work: ~%.0f s on one GPU, ~%.0f s on 8 "
