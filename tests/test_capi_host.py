@@ -163,3 +163,22 @@ def test_config_rejects_misordered_arm_pairs():
 def _one_region(cfg):
     genome = panel.lcg_genome(8000, 3)
     return panel.cut_region(genome, 3001, 3100, cfg)
+
+
+def test_batched_driver_source_edits_apply_exactly_once(tmp_path):
+    """mipgen_b200/batched/make_source.py: each of the five anchored edits matches the reference's mipgen.cpp exactly once (the script
+    exits otherwise) and leaves its marker in the patched copy.  Needs the reference sources: skipped on the GPU box."""
+    import subprocess
+    import sys
+    ref = "/root/reference/mipgen.cpp"
+    if not os.path.exists(ref):
+        pytest.skip("reference sources not present")
+    out = tmp_path / "mipgen_batched.cpp"
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "mipgen_b200", "batched", "make_source.py"), ref, str(out)], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    text = out.read_text(encoding="latin-1")
+    for marker in ('#include "mipgen_batched.h"', '#include "batched_members.inc"', "b200_tile_feature(feature);", "mipgen_b200_take_pending_svr(&b200_score)",
+                   "b200_write_fastqs(BWAFQ, ARMSFQ);", "if (b200_find_copy()) return;"):
+        assert text.count(marker) == 1, marker
+    # nothing else changed: the patched copy minus the inserted lines is a subsequence of the reference
+    assert len(text) < len(open(ref, encoding="latin-1").read()) + 1200
